@@ -1,0 +1,144 @@
+/*
+ * rt_engine.h -- C ABI of the B200 detection engine (librtb200.so).
+ *
+ * The reference (Nature40/pyradiotracking) is pure Python and has no FFI for this
+ * path; its boundary is the class radiotracking.analyze.SignalAnalyzer
+ * (radiotracking/analyze.py:20).  The entry points below are what a binding for the
+ * inside of SignalAnalyzer.process_samples (analyze.py:192-268) needs; each one names
+ * the reference lines it replaces.  The Python side of the binding (ctypes) is
+ * pyradiotracking_b200/engine.py; INTEGRATION.md shows the stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions: plain C types only; every function returns RT_OK (0) or a negative
+ * RT_ERR_* code and never throws; rt_last_error() returns a thread-local message for
+ * the last failure.  A handle is NOT thread-safe: one host thread per engine, like the
+ * reference's one-process-per-SDR model (radiotracking/__main__.py:94-130).
+ * There is no CPU fallback: without a CUDA device rt_engine_create fails.
+ */
+#ifndef RT_ENGINE_H
+#define RT_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_ABI_VERSION 1
+
+enum {
+    RT_OK = 0,
+    RT_ERR_INVALID = -1,      /* bad argument / unsupported configuration */
+    RT_ERR_CUDA = -2,         /* CUDA runtime error, no device, wrong architecture */
+    RT_ERR_OVERFLOW = -3,     /* more candidate records than max_records; none are lost silently */
+    RT_ERR_STATE = -4         /* call order violated (fetch without launch, ...) */
+};
+
+/* fft_impl selector: which spectrogram kernel runs (tests compare them). */
+enum { RT_FFT_AUTO = 0, RT_FFT_GENERIC = 1, RT_FFT_REG256 = 2 };
+
+/*
+ * Engine configuration = the analysis keys of SignalAnalyzer.__init__
+ * (analyze.py:62-129), already converted by the host the way the reference does it in
+ * float64 (analyze.py:113-116), for a batch of `n_streams` independent analyzers
+ * (one per SDR / recorded channel) that share sample rate and FFT settings.
+ */
+typedef struct rt_config {
+    int32_t abi_version;        /* RT_ABI_VERSION */
+    int32_t cuda_device;        /* ordinal */
+    int32_t n_streams;          /* analyzers in the batch (>= 1) */
+    int32_t nperseg;            /* fft_nperseg: power of two in [8, 4096] */
+    int64_t block_samples;      /* sdr_callback_length: complex samples per stream per call (analyze.py:108-109) */
+    double sample_rate;         /* fs */
+    const double *window;       /* nperseg values, as scipy get_window(fft_window, nperseg) returns them */
+    const double *signal_threshold; /* [n_streams] linear: 10**((signal_threshold_dbw + calibration_db)/10) (analyze.py:115) */
+    double snr_threshold;       /* linear: 10**(snr_threshold_db/10) (analyze.py:116) */
+    int32_t probe_stride;       /* max(1, int(signal_min_duration / (times[1]-times[0]))), float64 on the host (analyze.py:354,364) */
+    int32_t min_cols;           /* coarse duration gate in spectrogram columns; the exact float64 test */
+    int32_t max_cols;           /*   (analyze.py:419-433) is applied by the host on the returned records */
+    int32_t max_records;        /* capacity of one call's record list */
+    int32_t fft_impl;           /* RT_FFT_* */
+    int32_t reserved;
+} rt_config;
+
+/*
+ * One candidate detection = one maximal run of above-threshold cells that the
+ * reference's strided probe would visit (analyze.py:364-417), with the statistics
+ * of analyze.py:436-447 in linear units.  Columns index the current block's
+ * spectrogram; start < 0 reaches into the previous block (analyze.py:383-398).
+ * The host turns records into Signal objects (analyze.py:419-450).
+ */
+typedef struct rt_record {
+    int32_t stream;     /* analyzer index in the batch */
+    int32_t fi;         /* frequency bin, FFT order (no fftshift) */
+    int32_t start;      /* first column of the statistics window (inclusive) */
+    int32_t end;        /* last column + 1 */
+    float max_lin;      /* np.max(data) */
+    float row_mean;     /* freq_avg = np.mean(spectrogram[fi]) of the current block (analyze.py:374-375) */
+    double mean_lin;    /* np.mean(data) */
+    double std_db;      /* np.std(10*log10(data)) */
+} rt_record;
+
+typedef struct rt_engine rt_engine;
+
+/* Per-launch device timings accumulated while timing is enabled (milliseconds). */
+typedef struct rt_timing {
+    double spectrogram_ms;  /* uint8 IQ -> power cells + row sums (the dominant kernel) */
+    double rowmean_ms;
+    double probe_ms;
+    double extract_ms;
+    int64_t launches;       /* engine launches accumulated */
+    int64_t kernels;        /* CUDA kernels launched by those */
+} rt_timing;
+
+const char *rt_last_error(void);
+int rt_abi_version(void);
+/* Number of CUDA devices visible, or a negative RT_ERR_CUDA. */
+int rt_device_count(void);
+
+/* Replaces SignalAnalyzer.__init__'s analysis setup (analyze.py:108-129). */
+int rt_engine_create(const rt_config *cfg, rt_engine **out);
+void rt_engine_destroy(rt_engine *e);
+
+/* Launch on this CUDA stream (cudaStream_t) instead of the engine's own. */
+int rt_engine_set_stream(rt_engine *e, void *cuda_stream);
+
+/* Forget the carry of one stream (= a restarted analyzer: _spectrogram_last = None, analyze.py:128). */
+int rt_engine_reset_stream(rt_engine *e, int32_t stream);
+
+/*
+ * One callback for every stream of the batch (analyze.py:234-248 without the shadow
+ * filter): `iq` holds n_streams blocks of 2*block_samples interleaved uint8 I,Q bytes,
+ * stream s starting at iq + s*stream_stride_bytes.  iq_on_device != 0: `iq` is a device
+ * pointer (no copy); otherwise a host pointer (pinned or pageable) that is copied in.
+ * Blocks until done.  Records come back sorted by (stream, fi, start).
+ * On RT_ERR_OVERFLOW *n_out is the number that would have been needed.
+ */
+int rt_engine_process(rt_engine *e, const uint8_t *iq, int32_t iq_on_device, size_t stream_stride_bytes,
+                      rt_record *out, int32_t max_out, int32_t *n_out);
+
+/* The same in two halves: enqueue only (asynchronous) ... */
+int rt_engine_launch(rt_engine *e, const uint8_t *iq, int32_t iq_on_device, size_t stream_stride_bytes);
+/* ... then wait, copy back and sort the records of the last launch. */
+int rt_engine_fetch(rt_engine *e, rt_record *out, int32_t max_out, int32_t *n_out);
+
+/* Spectrogram geometry: *T = block_samples / nperseg columns per block. */
+int rt_engine_shape(const rt_engine *e, int32_t *n_streams, int32_t *nperseg, int32_t *T);
+
+/*
+ * Parity hooks (tests only): the power spectrogram of the last launch for one stream,
+ * as float32 [T][nperseg] (time-major, bins in FFT order), i.e. scipy's Sxx transposed
+ * (analyze.py:234-241); and the row means [nperseg] (analyze.py:375).
+ */
+int rt_engine_read_spectrogram(rt_engine *e, int32_t stream, float *out_T_by_nperseg);
+int rt_engine_read_row_means(rt_engine *e, int32_t stream, float *out_nperseg);
+
+/* CUDA-event timing of the individual kernels (bench.py roofline). */
+int rt_engine_enable_timing(rt_engine *e, int32_t on);
+int rt_engine_get_timing(rt_engine *e, rt_timing *out, int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_ENGINE_H */

@@ -1,0 +1,392 @@
+"""Host side of the detection hot path: the reference's `SignalAnalyzer` interface on top of
+the CUDA engine.
+
+* `SignalAnalyzer` keeps the reference constructor keys, the `process_samples(buffer, context)`
+  callback and the queue outputs (reference: radiotracking/analyze.py:20-280), so
+  `radiotracking/__main__.py:94-130` can start it in place of the reference class.
+* `BatchAnalyzer` is the same analysis for many independent streams on one GPU (one engine
+  call per block of every stream); `SignalAnalyzer` is a batch of one.
+
+Split of labour (SURVEY.md §7 hard part 3): the device does everything per cell and returns
+integer run limits `(fi, start, end)` plus linear statistics; everything that the reference
+computes in float64 *per signal* -- `times`, `freqs`, the probe stride, the duration test,
+timestamps, dB conversion (analyze.py:354, 419-450) -- is done here with the reference's own
+expressions so those fields are bit-identical.
+"""
+import datetime
+import logging
+import math
+import multiprocessing
+import signal as _signal
+import sys
+import time
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import engine as _engine
+from .messages import from_dB, message_types
+
+logger = logging.getLogger(__name__)
+UTC = datetime.timezone.utc
+
+
+def resolve_window(window, nperseg: int) -> np.ndarray:
+    """What scipy's `_triage_segments` makes of `fft_window` (analyze.py:236): a name or
+    `(name, param)` tuple goes through `scipy.signal.get_window` (periodic), an array is used
+    verbatim."""
+    if isinstance(window, (str, tuple)):
+        from scipy.signal import get_window
+
+        return np.asarray(get_window(window, nperseg), dtype=np.float64)
+    win = np.asarray(window, dtype=np.float64)
+    if win.ndim != 1:
+        raise ValueError("window must be 1-D")
+    if win.shape[0] != nperseg:
+        raise ValueError("window must have length of nperseg")
+    return win
+
+
+class DetectionPlan:
+    """Per-configuration float64 constants, computed exactly like scipy / the reference do."""
+
+    def __init__(self, sample_rate: float, nperseg: int, block_samples: int, min_duration_s: float, max_duration_s: float):
+        fs = sample_rate
+        self.nperseg = nperseg
+        self.block_samples = block_samples
+        # scipy _spectral_helper: freqs = fftfreq(nfft, 1/fs); time = arange(nperseg/2, N - nperseg/2 + 1, nperseg - noverlap)/fs
+        self.freqs = np.fft.fftfreq(nperseg, 1 / fs)
+        self.times = np.arange(nperseg / 2, block_samples - nperseg / 2 + 1, nperseg) / float(fs)
+        self.T = len(self.times)
+        if block_samples > 0 and self.T < 2:
+            # one column (or a block shorter than nperseg, which scipy shrinks to one column): analyze.py:354 indexes times[1]
+            raise IndexError("index 1 is out of bounds for axis 0 with size 1")
+        self.min_duration = min_duration_s
+        self.max_duration = max_duration_s
+        if self.T >= 2:
+            dt = self.times[1] - self.times[0]
+            self.min_num = min_duration_s / dt                       # analyze.py:354
+            self.stride = max(1, int(self.min_num))                  # analyze.py:364
+            # coarse gates for the device (+-1 column of slack around the float64 test below)
+            self.min_cols = max(0, int(math.floor(min_duration_s / dt)) - 1)
+            self.max_cols = int(math.ceil(max_duration_s / dt)) + 2
+        else:
+            self.stride, self.min_cols, self.max_cols = 1, 0, 2
+
+    def duration(self, start: int, end: int) -> Tuple[float, float]:
+        """(start_dt, duration_s) exactly as analyze.py:419-427."""
+        times = self.times
+        end_dt = times[end]
+        start_dt = -times[-start] if start < 0 else times[start]
+        return start_dt, end_dt - start_dt
+
+
+def _us(td: datetime.timedelta) -> int:
+    return (td.days * 86400 + td.seconds) * 1_000_000 + td.microseconds
+
+
+def shadow_mask(ts_us: np.ndarray, dur_us: np.ndarray, max_dbw: np.ndarray) -> np.ndarray:
+    """True where a signal is a shadow (analyze.py:283-313): some signal of the same list overlaps
+    it in time (closed intervals, microsecond datetimes) and is strictly louder.  No frequency term."""
+    n = len(ts_us)
+    out = np.zeros(n, dtype=bool)
+    if n == 0:
+        return out
+    te = ts_us + dur_us
+    step = max(1, (1 << 22) // n)
+    for i0 in range(0, n, step):
+        sl = slice(i0, min(n, i0 + step))
+        overlap = (ts_us[sl, None] <= te[None, :]) & (te[sl, None] >= ts_us[None, :])
+        out[sl] = (overlap & (max_dbw[None, :] > max_dbw[sl, None])).any(axis=1)
+    return out
+
+
+class BatchAnalyzer:
+    """`n` independent analyzers (same sample rate / FFT / duration keys, own device name and
+    calibration) evaluated together on one GPU."""
+
+    def __init__(self, devices: Sequence[str], calibration_db: Sequence[float], sample_rate: int, center_freq: int,
+                 fft_nperseg: int, fft_window, signal_min_duration_ms: float, signal_max_duration_ms: float,
+                 signal_threshold_dbw: float, snr_threshold_db: float, sdr_callback_length: Optional[int] = None,
+                 cuda_device: int = 0, max_records: int = 1 << 16, fft_impl: int = _engine.FFT_AUTO):
+        self.devices = [str(d) for d in devices]
+        self.n_streams = len(self.devices)
+        self.calibration_db = [float(c) for c in calibration_db]
+        if len(self.calibration_db) != self.n_streams:
+            raise ValueError("one calibration value per device")
+        self.sample_rate = sample_rate
+        self.center_freq = center_freq
+        self.fft_nperseg = fft_nperseg
+        self.fft_window = fft_window
+        self.block_samples = sample_rate if sdr_callback_length is None else sdr_callback_length   # analyze.py:108-109
+        self.signal_min_duration = signal_min_duration_ms / 1000                                    # analyze.py:113
+        self.signal_max_duration = signal_max_duration_ms / 1000                                    # analyze.py:114
+        self.signal_threshold = [from_dB(signal_threshold_dbw + c) for c in self.calibration_db]   # analyze.py:115
+        self.snr_threshold = from_dB(snr_threshold_db)                                              # analyze.py:116
+        self.plan = DetectionPlan(sample_rate, fft_nperseg, self.block_samples, self.signal_min_duration, self.signal_max_duration)
+        self.window = resolve_window(fft_window, fft_nperseg)
+        self.cuda_device = cuda_device
+        self.max_records = max_records
+        self.fft_impl = fft_impl
+        self._engine: Optional[_engine.Engine] = None
+        self.Signal, self.StateMessage = message_types()
+
+    # the engine is created on first use: after a fork, inside the analyzer process
+    @property
+    def engine(self) -> _engine.Engine:
+        if self._engine is None:
+            if self.plan.T < 2:
+                raise ValueError("block shorter than two FFT segments")
+            self._engine = _engine.Engine(
+                n_streams=self.n_streams, block_samples=self.block_samples, nperseg=self.fft_nperseg, window=self.window,
+                sample_rate=self.sample_rate, signal_threshold=self.signal_threshold, snr_threshold=self.snr_threshold,
+                probe_stride=self.plan.stride, min_cols=self.plan.min_cols, max_cols=self.plan.max_cols,
+                max_records=self.max_records, cuda_device=self.cuda_device, fft_impl=self.fft_impl)
+        return self._engine
+
+    def close(self):
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+
+    def reset_stream(self, stream: int):
+        """Forget the previous block of one stream (a restarted analyzer)."""
+        self.engine.reset_stream(stream)
+
+    # -- finaliser: records -> Signal objects ----------------------------------------------------
+    def finalize(self, records: np.ndarray, ts_start: Sequence[datetime.datetime]):
+        """-> per stream `(signals, keys)`: the reference's `extract_signals` output (analyze.py:419-450)
+        in its order (bin, then time) and the integer `(fi, start, end)` of each."""
+        plan = self.plan
+        out = [([], []) for _ in range(self.n_streams)]
+        Signal = self.Signal
+        for r in records:
+            s, fi, start, end = int(r["stream"]), int(r["fi"]), int(r["start"]), int(r["end"])
+            start_dt, duration_s = plan.duration(start, end)
+            if duration_s < self.signal_min_duration or duration_s > self.signal_max_duration:
+                continue
+            cal = self.calibration_db[s]
+            ts = ts_start[s] + datetime.timedelta(seconds=start_dt)
+            avg = float(r["mean_lin"])
+            freq_avg = float(r["row_mean"])
+            sig = Signal(
+                self.devices[s], ts.astimezone(UTC), plan.freqs[fi] + self.center_freq, datetime.timedelta(seconds=duration_s),
+                10 * np.log10(float(r["max_lin"])) - cal, 10 * np.log10(avg) - cal, float(r["std_db"]),
+                10 * np.log10(freq_avg), 10 * np.log10(avg / freq_avg))
+            out[s][0].append(sig)
+            out[s][1].append((fi, start, end))
+        return out
+
+    @staticmethod
+    def filter_shadow_signals(signals: list) -> list:
+        """analyze.py:315-328, vectorised."""
+        if len(signals) < 2:
+            return list(signals)
+        epoch = datetime.datetime(1970, 1, 1, tzinfo=UTC)
+        ts = np.array([_us(s.ts - epoch) for s in signals], dtype=np.int64)
+        du = np.array([_us(s.duration) for s in signals], dtype=np.int64)
+        mx = np.array([s.max for s in signals], dtype=np.float64)
+        shadow = shadow_mask(ts, du, mx)
+        return [s for s, sh in zip(signals, shadow) if not sh]
+
+    # -- one callback for every stream --------------------------------------------------------------
+    def process_blocks(self, iq, ts_start: Sequence[datetime.datetime]):
+        """`iq`: uint8 `[n_streams, 2*block_samples]` on the host, or a CUDA tensor of that shape.
+        -> per stream `(filtered_signals, all_signals, keys)`."""
+        records = self.engine.process(iq)
+        per_stream = self.finalize(records, ts_start)
+        return [(self.filter_shadow_signals(sigs), sigs, keys) for sigs, keys in per_stream]
+
+
+def iq_to_bytes(buffer: np.ndarray) -> np.ndarray:
+    """Inverse of pyrtlsdr's `packed_bytes_to_iq` (x = b/127.5 - 1): recover the uint8 I/Q bytes the
+    SDR delivered from the complex samples handed to `process_samples`.  The kernels consume raw
+    bytes; samples that are not on the 8-bit grid cannot have come from an RTL-SDR and are rejected."""
+    x = np.ascontiguousarray(buffer, dtype=np.complex128).view(np.float64)
+    b = (x + 1.0) * 127.5
+    q = np.rint(b)
+    if q.size and (np.max(np.abs(b - q)) > 1e-6 or q.min() < 0 or q.max() > 255):
+        raise ValueError("samples are not 8-bit RTL-SDR IQ (x = byte/127.5 - 1); use process_bytes with the raw buffer")
+    return q.astype(np.uint8)
+
+
+class SignalAnalyzer(multiprocessing.Process):
+    """Drop-in for `radiotracking.analyze.SignalAnalyzer` (analyze.py:20-129): same constructor keys,
+    same callback, same queue traffic; the spectrogram and the scans run on the GPU.
+
+    Extra keys (ignored by the reference thanks to its `**kwargs`): `cuda_device`.
+    """
+
+    def __init__(self, device: str, calibration_db: float, sample_rate: int, center_freq: int, gain: float,
+                 fft_nperseg: int, fft_window, signal_min_duration_ms: float, signal_max_duration_ms: float,
+                 signal_threshold_dbw: float, snr_threshold_db: float, verbose: int, sdr_max_restart: int,
+                 sdr_timeout_s: int, state_update_s: int, sdr_callback_length: int, signal_queue, last_data_ts,
+                 cuda_device: int = 0, **kwargs):
+        super().__init__()
+        self.device = device
+        self.calibration_db = calibration_db
+        try:
+            self.device_index = int(device)                         # analyze.py:88-91
+            logger.info(f"Using '{device}' as device index.")
+        except ValueError:
+            import rtlsdr                                           # analyze.py:93-99
+
+            try:
+                self.device_index = rtlsdr.RtlSdr.get_device_index_by_serial(device)
+                logger.info(f"Using '{device}' as serial number (index: {self.device_index}).")
+            except rtlsdr.rtlsdr.LibUSBError:
+                logger.warning(f"Device '{device}' could was not found, aborting.")
+                sys.exit(1)
+        self.sample_rate = sample_rate
+        self.center_freq = center_freq
+        try:
+            self.gain = float(gain)
+        except ValueError:
+            self.gain = gain
+        if sdr_callback_length is None:
+            sdr_callback_length = sample_rate
+        self.fft_nperseg = fft_nperseg
+        self.fft_window = fft_window
+        self.signal_min_duration = signal_min_duration_ms / 1000
+        self.signal_max_duration = signal_max_duration_ms / 1000
+        self.signal_threshold = from_dB(signal_threshold_dbw + calibration_db)
+        self.snr_threshold = from_dB(snr_threshold_db)
+        self.sdr_callback_length = sdr_callback_length
+        self.verbose = verbose
+        self.sdr_max_restart = sdr_max_restart
+        self.sdr_timeout_s = sdr_timeout_s
+        self.state_update_s = state_update_s
+        self.signal_queue = signal_queue
+        self.last_data_ts = last_data_ts
+        self.cuda_device = cuda_device
+        self._batch_args = dict(
+            devices=[device], calibration_db=[calibration_db], sample_rate=sample_rate, center_freq=center_freq,
+            fft_nperseg=fft_nperseg, fft_window=fft_window, signal_min_duration_ms=signal_min_duration_ms,
+            signal_max_duration_ms=signal_max_duration_ms, signal_threshold_dbw=signal_threshold_dbw,
+            snr_threshold_db=snr_threshold_db, sdr_callback_length=sdr_callback_length, cuda_device=cuda_device,
+            fft_impl=kwargs.get("fft_impl", _engine.FFT_AUTO))
+        self._batch: Optional[BatchAnalyzer] = None
+        self._ts = None
+        self._have_last = False         # stands in for `_spectrogram_last is not None` (the carry lives on the device)
+        self._alarm_armed = False
+        self.last_state = None
+        self.sdr = None
+        self._now = datetime.datetime.now
+        self.Signal, self.StateMessage = message_types()
+
+    @property
+    def batch(self) -> BatchAnalyzer:
+        if self._batch is None:
+            self._batch = BatchAnalyzer(**self._batch_args)
+        return self._batch
+
+    # -- process entry (analyze.py:131-157) ------------------------------------------------------
+    def run(self):
+        import rtlsdr
+
+        _signal.signal(_signal.SIGTERM, self.handle_signal)
+        _signal.signal(_signal.SIGINT, self.handle_signal)
+        logging.basicConfig(level=max(0, logging.WARN - (self.verbose * 10)))
+        sdr = rtlsdr.RtlSdr(self.device_index)
+        sdr.sample_rate = self.sample_rate
+        sdr.center_freq = self.center_freq
+        sdr.gain = float(self.gain)
+        sdr.set_agc_mode(False)
+        self.sdr = sdr
+        self.last_state = None
+        self.batch.engine                                       # CUDA context is created in this process
+        _signal.signal(_signal.SIGALRM, self.handle_signal)
+        _signal.alarm(self.sdr_timeout_s)
+        self._alarm_armed = True
+        # raw bytes: no complex128 round trip (the reference registers process_samples via read_samples_async)
+        self.sdr.read_bytes_async(self.process_bytes, 2 * self.sdr_callback_length)
+
+    def handle_signal(self, sig, frame):
+        """analyze.py:159-178."""
+        if sig == _signal.SIGALRM:
+            logger.warning("SDR %s received SIGALRM, last data received %s ago.", self.device,
+                           self._now() - self._ts if self._ts else "(no signal yet)")
+        elif sig == _signal.SIGTERM:
+            logger.warning("SDR %s received SIGTERM, terminating.", self.device)
+        elif sig == _signal.SIGINT:
+            return
+        self.update_state(self._now(), self.StateMessage.State.STOPPED)
+        self.sdr.cancel_read_async()
+
+    def update_state(self, ts: datetime.datetime, state):
+        """analyze.py:180-190: at most one message per state every `state_update_s`."""
+        if self.last_state and self.last_state.state == state:
+            if self.last_state.ts + datetime.timedelta(seconds=self.state_update_s) >= ts.astimezone(UTC):
+                return
+        self.last_state = self.StateMessage(self.device, ts.astimezone(UTC), state)
+        self.signal_queue.put(self.last_state)
+
+    # -- the callback (analyze.py:192-268) ---------------------------------------------------------
+    def process_samples(self, buffer: np.ndarray, context):
+        """Reference-compatible entry: complex samples as pyrtlsdr's `read_samples_async` delivers them."""
+        self.process_bytes(iq_to_bytes(buffer), context)
+
+    def process_bytes(self, buffer, context):
+        """Fast entry: the raw interleaved uint8 buffer of `read_bytes_async` (valid only during the call;
+        it is copied to the device before returning)."""
+        raw = np.frombuffer(buffer, dtype=np.uint8) if not isinstance(buffer, np.ndarray) else buffer
+        n_samples = raw.shape[0] // 2
+        ts_recv = self._now()
+        buffer_len_dt = datetime.timedelta(seconds=n_samples / self.sample_rate)
+        if self._alarm_armed:
+            _signal.alarm(self.sdr_timeout_s)                   # analyze.py:208
+        if not self.last_data_ts.value:
+            self.update_state(self._now(), self.StateMessage.State.STARTED)
+        else:
+            self.update_state(ts_recv, self.StateMessage.State.RUNNING)
+        self.last_data_ts.value = datetime.datetime.timestamp(ts_recv)
+        logger.info(f"SDR {self.device} received data at {self.last_data_ts.value}")
+
+        if not self._ts:                                        # analyze.py:217-221
+            self._ts = ts_recv
+        else:
+            self._ts += buffer_len_dt
+        clock_drift = (ts_recv - self._ts).total_seconds()
+        if clock_drift > 2 * buffer_len_dt.total_seconds():     # analyze.py:223-229
+            logger.warning(f"SDR {self.device} total clock drift ({clock_drift:.5f} s) is larger than two blocks, signal detection is degraded. Terminating...")
+            self.update_state(self._now(), self.StateMessage.State.STOPPED)
+            self.sdr.cancel_read_async()
+        ts_start = self._ts - buffer_len_dt
+
+        if n_samples == 0:                                      # scipy returns empty arrays, extract_signals returns [] (analyze.py:351)
+            return
+        if n_samples != self.sdr_callback_length:
+            # the reference indexes times[-start] of the CURRENT block into the previous one (analyze.py:423);
+            # a changing block length is undefined there, and the engine is sized for one length
+            raise ValueError(f"callback delivered {n_samples} samples, analyzer is configured for {self.sdr_callback_length}")
+
+        bench_start = time.time()
+        filtered, signals, _ = self.batch.process_blocks(raw.reshape(1, -1), [ts_start])[0]
+        bench_extract = time.time()
+        [self.consume_signal(s) for s in filtered]
+        bench_consume = time.time()
+        self._have_last = True
+        logger.info(
+            f"SDR {self.device} recv {n_samples}, clock drift: {clock_drift:.2f} s, "
+            f"filtered {len(filtered)} / {len(signals)} signals, block len: {buffer_len_dt.total_seconds() * 1000:.1f} ms, "
+            f"compute: {(bench_consume - bench_start) * 1000:.1f} ms")
+        logger.debug(f"timings - device+finalise: {(bench_extract - bench_start) * 1000:.1f} ms, "
+                     f"consume: {(bench_consume - bench_extract) * 1000:.1f} ms")
+
+    def consume_signal(self, signal):
+        """analyze.py:270-280."""
+        logger.debug(f"SDR {self.device} received {signal}")
+        self.signal_queue.put(signal)
+
+    # reference static helpers, kept for callers that use them directly (analyze.py:282-328)
+    @staticmethod
+    def is_shadow_of(sig, signals) -> Optional[int]:
+        for i, fsig in enumerate(signals):
+            if sig.ts > fsig.ts + fsig.duration or sig.ts + sig.duration < fsig.ts:
+                continue
+            if fsig.max > sig.max:
+                return i
+        return None
+
+    def filter_shadow_signals(self, signals):
+        return BatchAnalyzer.filter_shadow_signals(signals)

@@ -1,0 +1,809 @@
+// rt_engine.cu -- B200 (sm_100a) detection engine behind include/rt_engine.h.
+//
+// Path replaced: the inside of SignalAnalyzer.process_samples
+// (/root/reference/radiotracking/analyze.py:234-245): scipy.signal.spectrogram
+// (noverlap=0, two-sided, detrend='constant', density scaling) followed by
+// extract_signals' probe / backward / forward scans and per-signal statistics.
+//
+// Kernels (one launch each per engine call, all streams of the batch at once):
+//   spectro_*      uint8 IQ -> power cells S[stream][t][bin] (fp32) + per-chunk row sums
+//   row_mean       deterministic reduction of the chunk sums -> freq_avg[stream][bin]
+//   probe          one thread per (stream, bin, probe column k*stride): predicate test,
+//                  cheap pruning of short noise runs, survivors -> work list
+//   extract        one warp per work item: run limits by ballot, carry into the
+//                  previous block, coarse duration gate, statistics, record emission
+//
+// No CPU fallback and no library FFT: if this file is not built for the device present,
+// rt_engine_create fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rt_engine.h"
+#include "fft_regs.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(RT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));          \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+
+// analyze.py:370-379: a cell is part of a run unless it undershoots either threshold.
+__device__ __forceinline__ bool above(float p, float thr, float avg, float snr) {
+    return !(p < thr) && !(__fdiv_rn(p, avg) < snr);
+}
+
+// bin -> position inside one stored spectrogram column.  The register kernel stores the 16 bins a
+// thread owns (k1 + 16*k2) contiguously, so its layout is the 16x16 transpose of FFT order.
+template <bool PERM>
+__device__ __forceinline__ int bin_pos(int fi) {
+    return PERM ? (((fi & 15) << 4) | (fi >> 4)) : fi;
+}
+
+// ---------------------------------------------------------------------------------------------
+// spectrogram, generic: any power-of-two nperseg in [8, 4096]; Stockham radix-2 in shared memory
+// ---------------------------------------------------------------------------------------------
+struct SpectroArgs {
+    const uint8_t* iq;
+    size_t stream_stride;
+    int n, T, chunk_segs, n_chunks;
+    const float* win;      // window * sqrt(1/(fs*sum(w^2))) / 127.5
+    const float2* tw;      // exp(-2 pi i k / n)
+    float* S;              // [stream][T][n]
+    float* part;           // [stream][chunk][n]   (FFT bin order)
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT) spectro_generic(SpectroArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = a.n;
+    float2* buf0 = reinterpret_cast<float2*>(smem_raw);
+    float2* buf1 = buf0 + n;
+    float* rowacc = reinterpret_cast<float*>(buf1 + n);
+    int* sums = reinterpret_cast<int*>(rowacc + n);
+
+    const int tid = threadIdx.x;
+    const int s = blockIdx.y;
+    const int seg0 = blockIdx.x * a.chunk_segs;
+    const int seg1 = min(a.T, seg0 + a.chunk_segs);
+    for (int i = tid; i < n; i += NT) rowacc[i] = 0.f;
+
+    for (int seg = seg0; seg < seg1; ++seg) {
+        const uchar2* src = reinterpret_cast<const uchar2*>(a.iq + (size_t)s * a.stream_stride + (size_t)seg * 2 * n);
+        if (tid == 0) sums[0] = sums[1] = 0;
+        __syncthreads();
+        // scipy detrend='constant': the segment's complex mean; byte sums are exact integers
+        int sI = 0, sQ = 0;
+        for (int i = tid; i < n; i += NT) {
+            uchar2 v = src[i];
+            sI += v.x;
+            sQ += v.y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sI += __shfl_xor_sync(0xffffffffu, sI, o);
+            sQ += __shfl_xor_sync(0xffffffffu, sQ, o);
+        }
+        if ((tid & 31) == 0) {
+            atomicAdd(&sums[0], sI);
+            atomicAdd(&sums[1], sQ);
+        }
+        __syncthreads();
+        const float mI = (float)sums[0] / (float)n;   // exact: sum < 2^24, n a power of two
+        const float mQ = (float)sums[1] / (float)n;
+        for (int i = tid; i < n; i += NT) {
+            uchar2 v = src[i];
+            float w = a.win[i];
+            buf0[i] = make_float2(((float)v.x - mI) * w, ((float)v.y - mQ) * w);
+        }
+        __syncthreads();
+        float2* X = buf0;
+        float2* Y = buf1;
+        int st = 1, lst = 0;
+        for (int ncur = n; ncur > 1; ncur >>= 1, st <<= 1, ++lst) {
+            const int m = ncur >> 1;
+            for (int b = tid; b < (n >> 1); b += NT) {
+                const int p = b >> lst, q = b & (st - 1);
+                const float2 w = a.tw[p << lst];
+                const float2 u = X[q + st * p], v = X[q + st * (p + m)];
+                Y[q + st * 2 * p] = make_float2(u.x + v.x, u.y + v.y);
+                const float dr = u.x - v.x, di = u.y - v.y;
+                Y[q + st * (2 * p + 1)] = make_float2(dr * w.x - di * w.y, dr * w.y + di * w.x);
+            }
+            __syncthreads();
+            float2* t = X;
+            X = Y;
+            Y = t;
+        }
+        float* dst = a.S + ((size_t)s * a.T + seg) * n;
+        for (int i = tid; i < n; i += NT) {
+            const float2 x = X[i];
+            const float p = x.x * x.x + x.y * x.y;
+            dst[i] = p;
+            rowacc[i] += p;
+        }
+        __syncthreads();
+    }
+    float* pd = a.part + ((size_t)s * a.n_chunks + blockIdx.x) * n;
+    for (int i = tid; i < n; i += NT) pd[i] = rowacc[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// spectrogram, nperseg == 256: 16 threads per segment, 16x16 Cooley-Tukey held in registers,
+// one shared-memory transpose between the two radix-16 passes
+// ---------------------------------------------------------------------------------------------
+constexpr int R256_HW = 8;                 // half-warps (= segments in flight) per CTA
+constexpr int R256_THREADS = R256_HW * 16;
+constexpr int R256_RAW_STRIDE = 544;       // 512 B of IQ + 32 B pad: the two segments of a warp hit disjoint banks
+constexpr int R256_XROW = 36;              // floats per exchange row: 16 complex + 16 B pad (conflict-free LDS.128)
+
+__global__ void __launch_bounds__(R256_THREADS, 4) spectro_reg256(SpectroArgs a) {
+    __shared__ __align__(16) unsigned char raw[R256_HW][R256_RAW_STRIDE];
+    __shared__ __align__(16) float xch[R256_HW][16 * R256_XROW];
+
+    const int tid = threadIdx.x;
+    const int hw = tid >> 4, j = tid & 15;
+    const unsigned hmask = 0xffffu << (16 * (hw & 1));
+    const int s = blockIdx.y;
+    const int seg0 = blockIdx.x * a.chunk_segs;
+    const int seg1 = min(a.T, seg0 + a.chunk_segs);
+
+    float wj[16], twr[16], twi[16], acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        wj[i] = a.win[16 * i + j];                 // window at sample 16*n1 + j
+        const float2 t = a.tw[(j * i) & 255];      // W256^{j*k1}
+        twr[i] = t.x;
+        twi[i] = t.y;
+        acc[i] = 0.f;
+    }
+    const uint8_t* base = a.iq + (size_t)s * a.stream_stride;
+
+    for (int seg = seg0 + hw; seg < seg1; seg += R256_HW) {
+        const uint4* src = reinterpret_cast<const uint4*>(base + (size_t)seg * 512) + 2 * j;
+        const uint4 q0 = __ldg(src), q1 = __ldg(src + 1);
+        // detrend: exact byte sums of I and Q over the 256 samples (bytes: I0 Q0 I1 Q1 per word)
+        unsigned sI = 0, sQ = 0;
+        sI = __dp4a(q0.x, 0x00010001u, sI); sQ = __dp4a(q0.x, 0x01000100u, sQ);
+        sI = __dp4a(q0.y, 0x00010001u, sI); sQ = __dp4a(q0.y, 0x01000100u, sQ);
+        sI = __dp4a(q0.z, 0x00010001u, sI); sQ = __dp4a(q0.z, 0x01000100u, sQ);
+        sI = __dp4a(q0.w, 0x00010001u, sI); sQ = __dp4a(q0.w, 0x01000100u, sQ);
+        sI = __dp4a(q1.x, 0x00010001u, sI); sQ = __dp4a(q1.x, 0x01000100u, sQ);
+        sI = __dp4a(q1.y, 0x00010001u, sI); sQ = __dp4a(q1.y, 0x01000100u, sQ);
+        sI = __dp4a(q1.z, 0x00010001u, sI); sQ = __dp4a(q1.z, 0x01000100u, sQ);
+        sI = __dp4a(q1.w, 0x00010001u, sI); sQ = __dp4a(q1.w, 0x01000100u, sQ);
+        unsigned tot = sI | (sQ << 16);            // each total <= 255*256 < 2^16
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) tot += __shfl_xor_sync(hmask, tot, o, 16);
+        // 32768 + mean: exact in fp32 (mean is a multiple of 2^-8, ulp(2^15) = 2^-8)
+        const float cI = 32768.f + (float)(tot & 0xffffu) * 0.00390625f;
+        const float cQ = 32768.f + (float)(tot >> 16) * 0.00390625f;
+
+        __syncwarp(hmask);                          // the previous segment's readers are done
+        *reinterpret_cast<uint4*>(&raw[hw][32 * j]) = q0;
+        *reinterpret_cast<uint4*>(&raw[hw][32 * j + 16]) = q1;
+        __syncwarp(hmask);
+
+        rt::cf v[16];
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) {
+            const unsigned u = *reinterpret_cast<const unsigned short*>(&raw[hw][32 * n1 + 2 * j]);
+            // byte -> float without I2F: 0x4700bb00 is 32768 + b
+            const float fI = __uint_as_float(__byte_perm(u, 0x47000000u, 0x7604));
+            const float fQ = __uint_as_float(__byte_perm(u, 0x47000000u, 0x7614));
+            v[n1].re = (fI - cI) * wj[n1];
+            v[n1].im = (fQ - cQ) * wj[n1];
+        }
+        rt::dft16(v);                               // over n1 -> k1, for column n2 = j
+#pragma unroll
+        for (int k1 = 1; k1 < 16; ++k1) v[k1] = rt::cmul(v[k1], twr[k1], twi[k1]);
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1)
+            *reinterpret_cast<float2*>(&xch[hw][k1 * R256_XROW + 2 * j]) = make_float2(v[k1].re, v[k1].im);
+        __syncwarp(hmask);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float4 q = *reinterpret_cast<const float4*>(&xch[hw][j * R256_XROW + 4 * c]);
+            v[2 * c] = rt::cf{q.x, q.y};
+            v[2 * c + 1] = rt::cf{q.z, q.w};
+        }
+        rt::dft16(v);                               // over n2 -> k2, for k1 = j: bin = j + 16*k2
+        float p[16];
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) {
+            p[k2] = v[k2].re * v[k2].re + v[k2].im * v[k2].im;
+            acc[k2] += p[k2];
+        }
+        float4* dst = reinterpret_cast<float4*>(a.S + ((size_t)s * a.T + seg) * 256 + 16 * j);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dst[c] = make_float4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
+    }
+
+    // chunk row sums: fixed-order reduction over the half-warps, written in FFT bin order
+    __syncthreads();
+    float* red = &xch[0][0];
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) red[hw * 256 + 16 * j + k2] = acc[k2];
+    __syncthreads();
+    float* pd = a.part + ((size_t)s * a.n_chunks + blockIdx.x) * 256;
+    for (int fi = tid; fi < 256; fi += R256_THREADS) {
+        const int pos = bin_pos<true>(fi);
+        float t = 0.f;
+#pragma unroll
+        for (int h = 0; h < R256_HW; ++h) t += red[h * 256 + pos];
+        pd[fi] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// row means (analyze.py:374-375), deterministic
+// ---------------------------------------------------------------------------------------------
+__global__ void row_mean_kernel(const float* part, float* avg, int n, int n_chunks, int T, int total) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // stream*n + fi
+    if (idx >= total) return;
+    const int s = idx / n, fi = idx - s * n;
+    const float* p = part + (size_t)s * n_chunks * n + fi;
+    double t = 0.0;
+    for (int c = 0; c < n_chunks; ++c) t += (double)p[(size_t)c * n];
+    avg[idx] = (float)(t / (double)T);
+}
+
+// ---------------------------------------------------------------------------------------------
+// probe + extraction (analyze.py:354-447)
+// ---------------------------------------------------------------------------------------------
+struct ScanArgs {
+    const float* S;        // current block  [stream][T][n]
+    const float* Sprev;    // previous block
+    const float* avg;      // [stream][n]
+    const float* thr;      // [stream]
+    const int* has_prev;   // [stream]
+    float snr;
+    int n, T, stride, n_probes, min_cols, max_cols;
+    uint2* work;           // (stream << 16 | fi, ti)
+    int* counters;         // [0] work items, [1] records
+    rt_record* rec;
+    int max_records;
+};
+
+constexpr int PROBE_QUICK = 3;   // cells examined on each side before handing a probe hit to a warp
+
+template <bool PERM>
+__global__ void probe_kernel(ScanArgs a) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.n_probes * a.n) return;
+    const int k = idx / a.n, fi = idx - k * a.n;
+    const int s = blockIdx.y;
+    const int ti = k * a.stride;
+    const int pos = bin_pos<PERM>(fi);
+    const float* col = a.S + (size_t)s * a.T * a.n + pos;
+    const float thr = a.thr[s], avg = a.avg[s * a.n + fi], snr = a.snr;
+    if (!above(col[(size_t)ti * a.n], thr, avg, snr)) return;
+
+    // Most hits are 1-2 cell noise runs that the duration gate rejects anyway: resolve those here.
+    int lo = -1, hi = -1;             // nearest not-above cells, if found within PROBE_QUICK
+#pragma unroll
+    for (int d = 1; d <= PROBE_QUICK; ++d) {
+        const int t = ti - d;
+        if (t < 0) break;             // run reaches column 0: carry logic, leave it to the warp
+        if (!above(col[(size_t)t * a.n], thr, avg, snr)) { lo = t; break; }
+    }
+#pragma unroll
+    for (int d = 1; d <= PROBE_QUICK; ++d) {
+        const int t = ti + d;
+        if (t >= a.T) return;         // run touches the block end: dropped (analyze.py:415-417)
+        if (!above(col[(size_t)t * a.n], thr, avg, snr)) { hi = t; break; }
+    }
+    if (lo >= 0 && hi >= 0 && hi - lo < a.min_cols) return;   // window = [lo, hi): too short
+    const int slot = atomicAdd(&a.counters[0], 1);
+    a.work[slot] = make_uint2(((unsigned)s << 16) | (unsigned)fi, (unsigned)ti);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <bool PERM>
+__global__ void extract_kernel(ScanArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int n_work = a.counters[0];
+    const int T = a.T, n = a.n;
+
+    for (int item = warp; item < n_work; item += n_warps) {
+        const uint2 wk = a.work[item];
+        const int s = wk.x >> 16, fi = wk.x & 0xffff, ti = (int)wk.y;
+        const int pos = bin_pos<PERM>(fi);
+        const float* col = a.S + (size_t)s * T * n + pos;
+        const float* pcol = a.Sprev + (size_t)s * T * n + pos;
+        const float thr = a.thr[s], avg = a.avg[s * n + fi], snr = a.snr;
+
+        // ---- backward: nearest not-above cell in [ti - stride, ti).  If there is none and the
+        // previous probe column exists, that probe already owns this run (ti_skip, analyze.py:366).
+        const int lo_lim = max(ti - a.stride, 0);
+        int nb = -1;
+        for (int base = ti - 1; base >= lo_lim && nb < 0; base -= 32) {
+            const int t = base - lane;
+            const bool valid = t >= lo_lim;
+            const bool ab = valid ? above(col[(size_t)t * n], thr, avg, snr) : true;
+            const unsigned m = __ballot_sync(0xffffffffu, valid && !ab);
+            if (m) nb = base - (__ffs(m) - 1);
+        }
+        int start;
+        if (nb >= 0) {
+            start = nb;                                  // the not-above cell is part of the window
+        } else if (ti - a.stride >= 0) {
+            continue;                                    // an earlier probe lies in the same run
+        } else if (!a.has_prev[s]) {
+            start = 0;                                   // analyze.py:382: start_min = 0
+        } else {
+            // analyze.py:383-398: walk into the previous block, tested against the CURRENT row mean;
+            // start_min = -T + 1 is never tested itself.
+            const int jmax = T - 2;                      // cells last[T-1] ... last[2]
+            const int jcap = min(jmax, a.max_cols + 2);
+            int jf = 0;
+            for (int base = 1; base <= jcap && jf == 0; base += 32) {
+                const int jj = base + lane;
+                const bool valid = jj <= jcap;
+                const bool ab = valid ? above(pcol[(size_t)(T - jj) * n], thr, avg, snr) : true;
+                const unsigned m = __ballot_sync(0xffffffffu, valid && !ab);
+                if (m) jf = base + (__ffs(m) - 1);
+            }
+            if (jf > 0) start = -jf;
+            else if (jcap == jmax) start = -(T - 1);     // ran into start_min
+            else continue;                               // longer than max_cols: fails the duration test
+        }
+
+        // ---- forward: first not-above cell after ti (analyze.py:401-412)
+        int end = -1;
+        const int span_cap = a.max_cols + 2;             // beyond this the duration test fails anyway
+        bool too_long = false;
+        for (int base = ti + 1; base < T && end < 0; base += 32) {
+            if (base - start > span_cap) { too_long = true; break; }
+            const int t = base + lane;
+            const bool valid = t < T;
+            const bool ab = valid ? above(col[(size_t)t * n], thr, avg, snr) : true;
+            const unsigned m = __ballot_sync(0xffffffffu, valid && !ab);
+            if (m) end = base + (__ffs(m) - 1);
+        }
+        if (too_long || end < 0) continue;               // end == T: dropped, re-found from the next block
+        const int cols = end - start + (start < 0 ? 1 : 0);
+        if (cols < a.min_cols || cols > a.max_cols) continue;
+
+        // ---- statistics over data = [start, end) (analyze.py:436-447), float64 accumulation
+        const int cnt = end - start;
+        float mx = 0.f;
+        double sum = 0.0, sdb = 0.0;
+        for (int i = start + lane; i < end; i += 32) {
+            const float p = i < 0 ? pcol[(size_t)(T + i) * n] : col[(size_t)i * n];
+            mx = fmaxf(mx, p);
+            sum += (double)p;
+            sdb += 10.0 * log10((double)p);
+        }
+        mx = warp_max(mx);
+        sum = warp_sum(sum);
+        sdb = warp_sum(sdb);
+        const double mdb = sdb / cnt;
+        double ss = 0.0;
+        for (int i = start + lane; i < end; i += 32) {
+            const float p = i < 0 ? pcol[(size_t)(T + i) * n] : col[(size_t)i * n];
+            const double d = 10.0 * log10((double)p) - mdb;
+            ss += d * d;
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) {
+            const int slot = atomicAdd(&a.counters[1], 1);
+            if (slot < a.max_records) {
+                rt_record r;
+                r.stream = s; r.fi = fi; r.start = start; r.end = end;
+                r.max_lin = mx; r.row_mean = avg;
+                r.mean_lin = sum / cnt;
+                r.std_db = sqrt(ss / cnt);
+                a.rec[slot] = r;
+            }
+        }
+    }
+}
+
+// un-permute one stored column set for the parity hook
+__global__ void unpermute_kernel(const float* S, float* out, int T, int total) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int t = idx >> 8, fi = idx & 255;
+    out[idx] = S[(size_t)t * 256 + bin_pos<true>(fi)];
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct rt_engine {
+    rt_config cfg{};
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int n = 0, T = 0, n_streams = 0, n_chunks = 0, chunk_segs = 0, n_probes = 0;
+    bool reg256 = false;
+    float* d_win = nullptr;
+    float2* d_tw = nullptr;
+    float* d_S[2] = {nullptr, nullptr};
+    int cur = 0;
+    float* d_part = nullptr;
+    float* d_avg = nullptr;
+    float* d_thr = nullptr;
+    int* d_hasprev = nullptr;
+    std::vector<int> h_hasprev;
+    bool hasprev_dirty = true;
+    uint8_t* d_stage = nullptr;
+    size_t stage_stride = 0;
+    uint2* d_work = nullptr;
+    int* d_counters = nullptr;
+    rt_record* d_rec = nullptr;
+    rt_record* h_rec = nullptr;     // pinned
+    int* h_counters = nullptr;      // pinned
+    float* d_tmp = nullptr;         // parity hook scratch
+    bool launched = false;
+    // timing
+    bool timing = false;
+    struct EvSet { cudaEvent_t ev[5]; };
+    std::vector<EvSet> ev_pool;
+    size_t ev_used = 0;
+    rt_timing acc{};
+};
+
+namespace {
+
+int harvest_timing(rt_engine* e) {
+    if (e->ev_used == 0) return RT_OK;
+    CU(cudaStreamSynchronize(e->stream));
+    for (size_t i = 0; i < e->ev_used; ++i) {
+        float ms[4];
+        for (int k = 0; k < 4; ++k) CU(cudaEventElapsedTime(&ms[k], e->ev_pool[i].ev[k], e->ev_pool[i].ev[k + 1]));
+        e->acc.spectrogram_ms += ms[0];
+        e->acc.rowmean_ms += ms[1];
+        e->acc.probe_ms += ms[2];
+        e->acc.extract_ms += ms[3];
+    }
+    e->ev_used = 0;
+    return RT_OK;
+}
+
+void free_engine(rt_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->dev);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (auto& s : e->ev_pool)
+        for (auto& ev : s.ev) cudaEventDestroy(ev);
+    cudaFree(e->d_win); cudaFree(e->d_tw); cudaFree(e->d_S[0]); cudaFree(e->d_S[1]);
+    cudaFree(e->d_part); cudaFree(e->d_avg); cudaFree(e->d_thr); cudaFree(e->d_hasprev);
+    cudaFree(e->d_stage); cudaFree(e->d_work); cudaFree(e->d_counters); cudaFree(e->d_rec); cudaFree(e->d_tmp);
+    if (e->h_rec) cudaFreeHost(e->h_rec);
+    if (e->h_counters) cudaFreeHost(e->h_counters);
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rt_last_error(void) { return g_err.c_str(); }
+int rt_abi_version(void) { return RT_ABI_VERSION; }
+
+int rt_device_count(void) {
+    int n = 0;
+    cudaError_t err = cudaGetDeviceCount(&n);
+    if (err != cudaSuccess) return fail(RT_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(err));
+    return n;
+}
+
+int rt_engine_create(const rt_config* cfg, rt_engine** out) {
+    if (!cfg || !out) return fail(RT_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != RT_ABI_VERSION) return fail(RT_ERR_INVALID, "rt_config.abi_version mismatch");
+    const int n = cfg->nperseg;
+    if (n < 8 || n > 4096 || (n & (n - 1))) return fail(RT_ERR_INVALID, "nperseg must be a power of two in [8, 4096]");
+    if (cfg->n_streams < 1 || cfg->n_streams > 65535) return fail(RT_ERR_INVALID, "n_streams must be in [1, 65535]");
+    if (!cfg->window || !cfg->signal_threshold) return fail(RT_ERR_INVALID, "window / signal_threshold missing");
+    if (cfg->block_samples / n < 2) return fail(RT_ERR_INVALID, "block_samples must hold at least two segments (analyze.py:354 indexes times[1])");
+    if (cfg->block_samples / n > (1 << 24)) return fail(RT_ERR_INVALID, "block too long");
+    if (cfg->probe_stride < 1 || cfg->min_cols < 0 || cfg->max_cols < cfg->min_cols || cfg->max_records < 1)
+        return fail(RT_ERR_INVALID, "probe_stride / min_cols / max_cols / max_records out of range");
+    if (!(cfg->sample_rate > 0) || !(cfg->snr_threshold >= 0)) return fail(RT_ERR_INVALID, "sample_rate / snr_threshold out of range");
+
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (cfg->cuda_device < 0 || cfg->cuda_device >= ndev) return fail(RT_ERR_CUDA, "no such CUDA device (this engine has no CPU fallback)");
+    CU(cudaSetDevice(cfg->cuda_device));
+    cudaFuncAttributes fa;
+    cudaError_t ferr = cudaFuncGetAttributes(&fa, row_mean_kernel);
+    if (ferr != cudaSuccess)
+        return fail(RT_ERR_CUDA, std::string("kernels not loadable on this device (built for sm_100a only): ") + cudaGetErrorString(ferr));
+
+    rt_engine* e = new rt_engine();
+    e->cfg = *cfg;
+    e->dev = cfg->cuda_device;
+    e->n = n;
+    e->T = (int)(cfg->block_samples / n);
+    e->n_streams = cfg->n_streams;
+    e->n_probes = (e->T + cfg->probe_stride - 1) / cfg->probe_stride;
+    if (cfg->fft_impl == RT_FFT_REG256 && n != 256) { delete e; return fail(RT_ERR_INVALID, "RT_FFT_REG256 needs nperseg == 256"); }
+    e->reg256 = (n == 256) && (cfg->fft_impl != RT_FFT_GENERIC);
+    e->chunk_segs = e->reg256 ? 64 : 32;
+    e->n_chunks = (e->T + e->chunk_segs - 1) / e->chunk_segs;
+
+#define CUE(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            free_engine(e);                                                                        \
+            return fail(RT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));          \
+        }                                                                                          \
+    } while (0)
+
+    CUE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    e->own_stream = true;
+
+    // window with the density scaling and the 1/127.5 byte scale folded in:
+    // S = |FFT(w (x - mean))|^2 / (fs sum w^2),  x = b/127.5 - 1  =>  S = |FFT(w' (b - mean_b))|^2
+    double sw2 = 0.0;
+    for (int i = 0; i < n; ++i) sw2 += cfg->window[i] * cfg->window[i];
+    if (!(sw2 > 0)) { free_engine(e); return fail(RT_ERR_INVALID, "window has no energy"); }
+    const double amp = std::sqrt(1.0 / (cfg->sample_rate * sw2)) / 127.5;
+    std::vector<float> hwin(n);
+    for (int i = 0; i < n; ++i) hwin[i] = (float)(cfg->window[i] * amp);
+    std::vector<float2> htw(n);
+    for (int k = 0; k < n; ++k) {
+        const double ang = -2.0 * M_PI * (double)k / (double)n;
+        htw[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+    }
+    std::vector<float> hthr(e->n_streams);
+    for (int s = 0; s < e->n_streams; ++s) hthr[s] = (float)cfg->signal_threshold[s];
+
+    const size_t cells = (size_t)e->n_streams * e->T * n;
+    const size_t max_work = (size_t)e->n_streams * n * e->n_probes;
+    CUE(cudaMalloc(&e->d_win, n * sizeof(float)));
+    CUE(cudaMalloc(&e->d_tw, n * sizeof(float2)));
+    CUE(cudaMalloc(&e->d_S[0], cells * sizeof(float)));
+    CUE(cudaMalloc(&e->d_S[1], cells * sizeof(float)));
+    CUE(cudaMalloc(&e->d_part, (size_t)e->n_streams * e->n_chunks * n * sizeof(float)));
+    CUE(cudaMalloc(&e->d_avg, (size_t)e->n_streams * n * sizeof(float)));
+    CUE(cudaMalloc(&e->d_thr, e->n_streams * sizeof(float)));
+    CUE(cudaMalloc(&e->d_hasprev, e->n_streams * sizeof(int)));
+    CUE(cudaMalloc(&e->d_work, max_work * sizeof(uint2)));
+    CUE(cudaMalloc(&e->d_counters, 2 * sizeof(int)));
+    CUE(cudaMalloc(&e->d_rec, (size_t)cfg->max_records * sizeof(rt_record)));
+    CUE(cudaMallocHost(&e->h_rec, (size_t)cfg->max_records * sizeof(rt_record)));
+    CUE(cudaMallocHost(&e->h_counters, 2 * sizeof(int)));
+    CUE(cudaMemcpy(e->d_win, hwin.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    CUE(cudaMemcpy(e->d_tw, htw.data(), n * sizeof(float2), cudaMemcpyHostToDevice));
+    CUE(cudaMemcpy(e->d_thr, hthr.data(), e->n_streams * sizeof(float), cudaMemcpyHostToDevice));
+    e->h_hasprev.assign(e->n_streams, 0);
+    e->hasprev_dirty = true;
+    if (!e->reg256) {
+        const size_t smem = (size_t)n * (2 * sizeof(float2) + sizeof(float)) + 16;
+        CUE(cudaFuncSetAttribute(spectro_generic<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+#undef CUE
+    *out = e;
+    return RT_OK;
+}
+
+void rt_engine_destroy(rt_engine* e) { free_engine(e); }
+
+int rt_engine_set_stream(rt_engine* e, void* cuda_stream) {
+    if (!e) return fail(RT_ERR_INVALID, "null engine");
+    CU(cudaSetDevice(e->dev));
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->own_stream) {
+        CU(cudaStreamDestroy(e->stream));
+        e->own_stream = false;
+    }
+    e->stream = (cudaStream_t)cuda_stream;
+    return RT_OK;
+}
+
+int rt_engine_reset_stream(rt_engine* e, int32_t stream) {
+    if (!e || stream < 0 || stream >= e->n_streams) return fail(RT_ERR_INVALID, "bad stream index");
+    e->h_hasprev[stream] = 0;
+    e->hasprev_dirty = true;
+    return RT_OK;
+}
+
+int rt_engine_shape(const rt_engine* e, int32_t* n_streams, int32_t* nperseg, int32_t* T) {
+    if (!e) return fail(RT_ERR_INVALID, "null engine");
+    if (n_streams) *n_streams = e->n_streams;
+    if (nperseg) *nperseg = e->n;
+    if (T) *T = e->T;
+    return RT_OK;
+}
+
+int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size_t stream_stride_bytes) {
+    if (!e || !iq) return fail(RT_ERR_INVALID, "null argument");
+    const size_t block_bytes = 2 * (size_t)e->cfg.block_samples;
+    if (stream_stride_bytes < block_bytes && e->n_streams > 1) return fail(RT_ERR_INVALID, "stream_stride_bytes smaller than one block");
+    CU(cudaSetDevice(e->dev));
+    cudaStream_t st = e->stream;
+
+    const uint8_t* d_iq = iq;
+    size_t stride = stream_stride_bytes;
+    if (!iq_on_device) {
+        if (!e->d_stage) {
+            e->stage_stride = (block_bytes + 255) & ~(size_t)255;
+            CU(cudaMalloc(&e->d_stage, e->stage_stride * e->n_streams));
+        }
+        CU(cudaMemcpy2DAsync(e->d_stage, e->stage_stride, iq, stream_stride_bytes, block_bytes, e->n_streams,
+                             cudaMemcpyHostToDevice, st));
+        d_iq = e->d_stage;
+        stride = e->stage_stride;
+    }
+    if (e->hasprev_dirty) {
+        CU(cudaMemcpyAsync(e->d_hasprev, e->h_hasprev.data(), e->n_streams * sizeof(int), cudaMemcpyHostToDevice, st));
+        e->hasprev_dirty = false;
+    }
+    CU(cudaMemsetAsync(e->d_counters, 0, 2 * sizeof(int), st));
+
+    rt_engine::EvSet* evs = nullptr;
+    if (e->timing) {
+        if (e->ev_used == e->ev_pool.size()) {
+            if (e->ev_pool.size() >= 4096) { int rc = harvest_timing(e); if (rc) return rc; }
+            else {
+                rt_engine::EvSet s;
+                for (auto& ev : s.ev) CU(cudaEventCreate(&ev));
+                e->ev_pool.push_back(s);
+            }
+        }
+        evs = &e->ev_pool[e->ev_used++];
+        CU(cudaEventRecord(evs->ev[0], st));
+    }
+
+    const int next = e->cur ^ 1;
+    SpectroArgs sa;
+    sa.iq = d_iq; sa.stream_stride = stride; sa.n = e->n; sa.T = e->T;
+    sa.chunk_segs = e->chunk_segs; sa.n_chunks = e->n_chunks;
+    sa.win = e->d_win; sa.tw = e->d_tw; sa.S = e->d_S[next]; sa.part = e->d_part;
+    const bool aligned = (((uintptr_t)d_iq | stride) & 15) == 0;
+    const bool use_reg = e->reg256 && aligned;
+    if (e->reg256 && !aligned) return fail(RT_ERR_INVALID, "register FFT path needs 16-byte aligned IQ and stream stride");
+    dim3 grid(e->n_chunks, e->n_streams);
+    if (use_reg) {
+        spectro_reg256<<<grid, R256_THREADS, 0, st>>>(sa);
+    } else {
+        const size_t smem = (size_t)e->n * (2 * sizeof(float2) + sizeof(float)) + 16;
+        spectro_generic<256><<<grid, 256, smem, st>>>(sa);
+    }
+    CU(cudaGetLastError());
+    if (evs) CU(cudaEventRecord(evs->ev[1], st));
+
+    const int total = e->n_streams * e->n;
+    row_mean_kernel<<<(total + 127) / 128, 128, 0, st>>>(e->d_part, e->d_avg, e->n, e->n_chunks, e->T, total);
+    CU(cudaGetLastError());
+    if (evs) CU(cudaEventRecord(evs->ev[2], st));
+
+    ScanArgs sc;
+    sc.S = e->d_S[next]; sc.Sprev = e->d_S[e->cur]; sc.avg = e->d_avg; sc.thr = e->d_thr; sc.has_prev = e->d_hasprev;
+    sc.snr = (float)e->cfg.snr_threshold;
+    sc.n = e->n; sc.T = e->T; sc.stride = e->cfg.probe_stride; sc.n_probes = e->n_probes;
+    sc.min_cols = e->cfg.min_cols; sc.max_cols = e->cfg.max_cols;
+    sc.work = e->d_work; sc.counters = e->d_counters; sc.rec = e->d_rec; sc.max_records = e->cfg.max_records;
+    dim3 pgrid((e->n_probes * e->n + 255) / 256, e->n_streams);
+    if (use_reg) probe_kernel<true><<<pgrid, 256, 0, st>>>(sc);
+    else probe_kernel<false><<<pgrid, 256, 0, st>>>(sc);
+    CU(cudaGetLastError());
+    if (evs) CU(cudaEventRecord(evs->ev[3], st));
+    if (use_reg) extract_kernel<true><<<296, 256, 0, st>>>(sc);
+    else extract_kernel<false><<<296, 256, 0, st>>>(sc);
+    CU(cudaGetLastError());
+    if (evs) CU(cudaEventRecord(evs->ev[4], st));
+
+    e->cur = next;
+    for (auto& h : e->h_hasprev)
+        if (!h) { h = 1; e->hasprev_dirty = true; }
+    e->launched = true;
+    e->acc.launches += 1;
+    e->acc.kernels += 4;
+    return RT_OK;
+}
+
+int rt_engine_fetch(rt_engine* e, rt_record* out, int32_t max_out, int32_t* n_out) {
+    if (!e || !n_out) return fail(RT_ERR_INVALID, "null argument");
+    if (!e->launched) return fail(RT_ERR_STATE, "rt_engine_fetch without rt_engine_launch");
+    CU(cudaSetDevice(e->dev));
+    CU(cudaMemcpyAsync(e->h_counters, e->d_counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    const int nrec = e->h_counters[1];
+    *n_out = nrec;
+    if (nrec > e->cfg.max_records) return fail(RT_ERR_OVERFLOW, "more candidate records than rt_config.max_records");
+    if (nrec > max_out || (nrec > 0 && !out)) return fail(RT_ERR_OVERFLOW, "output buffer smaller than the number of records");
+    if (nrec > 0) {
+        CU(cudaMemcpyAsync(e->h_rec, e->d_rec, (size_t)nrec * sizeof(rt_record), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        std::sort(e->h_rec, e->h_rec + nrec, [](const rt_record& x, const rt_record& y) {
+            if (x.stream != y.stream) return x.stream < y.stream;
+            if (x.fi != y.fi) return x.fi < y.fi;
+            return x.start < y.start;
+        });
+        std::memcpy(out, e->h_rec, (size_t)nrec * sizeof(rt_record));
+    }
+    return RT_OK;
+}
+
+int rt_engine_process(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size_t stream_stride_bytes,
+                      rt_record* out, int32_t max_out, int32_t* n_out) {
+    int rc = rt_engine_launch(e, iq, iq_on_device, stream_stride_bytes);
+    if (rc != RT_OK) return rc;
+    return rt_engine_fetch(e, out, max_out, n_out);
+}
+
+int rt_engine_read_spectrogram(rt_engine* e, int32_t stream, float* out) {
+    if (!e || !out || stream < 0 || stream >= e->n_streams) return fail(RT_ERR_INVALID, "bad argument");
+    if (!e->launched) return fail(RT_ERR_STATE, "no launch yet");
+    CU(cudaSetDevice(e->dev));
+    const size_t cells = (size_t)e->T * e->n;
+    const float* src = e->d_S[e->cur] + (size_t)stream * cells;
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->reg256) {
+        if (!e->d_tmp) CU(cudaMalloc(&e->d_tmp, cells * sizeof(float)));
+        unpermute_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, e->stream>>>(src, e->d_tmp, e->T, (int)cells);
+        CU(cudaGetLastError());
+        src = e->d_tmp;
+    }
+    CU(cudaMemcpyAsync(out, src, cells * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return RT_OK;
+}
+
+int rt_engine_read_row_means(rt_engine* e, int32_t stream, float* out) {
+    if (!e || !out || stream < 0 || stream >= e->n_streams) return fail(RT_ERR_INVALID, "bad argument");
+    if (!e->launched) return fail(RT_ERR_STATE, "no launch yet");
+    CU(cudaSetDevice(e->dev));
+    CU(cudaMemcpyAsync(out, e->d_avg + (size_t)stream * e->n, e->n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return RT_OK;
+}
+
+int rt_engine_enable_timing(rt_engine* e, int32_t on) {
+    if (!e) return fail(RT_ERR_INVALID, "null engine");
+    if (!on) { int rc = harvest_timing(e); if (rc) return rc; }
+    e->timing = on != 0;
+    return RT_OK;
+}
+
+int rt_engine_get_timing(rt_engine* e, rt_timing* out, int32_t reset) {
+    if (!e || !out) return fail(RT_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(e->dev));
+    int rc = harvest_timing(e);
+    if (rc) return rc;
+    *out = e->acc;
+    if (reset) e->acc = rt_timing{};
+    return RT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,228 @@
+"""ctypes binding of the C ABI in include/rt_engine.h (librtb200.so, sm_100a CUDA).
+
+This is the thin host layer between `SignalAnalyzer` and the kernels.  There is no
+CPU fallback: if the shared library is missing or no CUDA device is present, creating
+an `Engine` raises.
+"""
+import ctypes
+import os
+from typing import Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import build as _build
+
+RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_OVERFLOW, RT_ERR_STATE = 0, -1, -2, -3, -4
+RT_ABI_VERSION = 1
+FFT_AUTO, FFT_GENERIC, FFT_REG256 = 0, 1, 2
+
+# every symbol include/rt_engine.h declares
+EXPORTS = (
+    "rt_last_error", "rt_abi_version", "rt_device_count", "rt_engine_create", "rt_engine_destroy",
+    "rt_engine_set_stream", "rt_engine_reset_stream", "rt_engine_process", "rt_engine_launch", "rt_engine_fetch",
+    "rt_engine_shape", "rt_engine_read_spectrogram", "rt_engine_read_row_means", "rt_engine_enable_timing",
+    "rt_engine_get_timing",
+)
+
+
+class RtConfig(ctypes.Structure):
+    _fields_ = [
+        ("abi_version", ctypes.c_int32), ("cuda_device", ctypes.c_int32), ("n_streams", ctypes.c_int32),
+        ("nperseg", ctypes.c_int32), ("block_samples", ctypes.c_int64), ("sample_rate", ctypes.c_double),
+        ("window", ctypes.POINTER(ctypes.c_double)), ("signal_threshold", ctypes.POINTER(ctypes.c_double)),
+        ("snr_threshold", ctypes.c_double), ("probe_stride", ctypes.c_int32), ("min_cols", ctypes.c_int32),
+        ("max_cols", ctypes.c_int32), ("max_records", ctypes.c_int32), ("fft_impl", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
+class RtTiming(ctypes.Structure):
+    _fields_ = [
+        ("spectrogram_ms", ctypes.c_double), ("rowmean_ms", ctypes.c_double), ("probe_ms", ctypes.c_double),
+        ("extract_ms", ctypes.c_double), ("launches", ctypes.c_int64), ("kernels", ctypes.c_int64),
+    ]
+
+
+# rt_record, 40 bytes
+RECORD_DTYPE = np.dtype([
+    ("stream", "<i4"), ("fi", "<i4"), ("start", "<i4"), ("end", "<i4"),
+    ("max_lin", "<f4"), ("row_mean", "<f4"), ("mean_lin", "<f8"), ("std_db", "<f8"),
+])
+assert RECORD_DTYPE.itemsize == 40
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"rt_engine error {code}: {msg}")
+        self.code = code
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen librtb200.so (building it first if it has never been built and nvcc is here)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        _build.build()          # raises if nvcc is missing: there is nothing to fall back to
+    lib = ctypes.CDLL(path)
+    lib.rt_last_error.restype = ctypes.c_char_p
+    lib.rt_engine_create.argtypes = [ctypes.POINTER(RtConfig), ctypes.POINTER(ctypes.c_void_p)]
+    lib.rt_engine_destroy.argtypes = [ctypes.c_void_p]
+    lib.rt_engine_destroy.restype = None
+    lib.rt_engine_set_stream.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.rt_engine_reset_stream.argtypes = [ctypes.c_void_p, ctypes.c_int32]
+    lib.rt_engine_process.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_size_t,
+                                      ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
+    lib.rt_engine_launch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_size_t]
+    lib.rt_engine_fetch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
+    lib.rt_engine_shape.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int32)] * 3
+    lib.rt_engine_read_spectrogram.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]
+    lib.rt_engine_read_row_means.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]
+    lib.rt_engine_enable_timing.argtypes = [ctypes.c_void_p, ctypes.c_int32]
+    lib.rt_engine_get_timing.argtypes = [ctypes.c_void_p, ctypes.POINTER(RtTiming), ctypes.c_int32]
+    if lib.rt_abi_version() != RT_ABI_VERSION:
+        raise ImportError(f"{path}: ABI {lib.rt_abi_version()} != {RT_ABI_VERSION}; rebuild (python -m pyradiotracking_b200.build --force)")
+    _lib = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc != RT_OK:
+        raise EngineError(rc, load_library().rt_last_error().decode("utf-8", "replace"))
+
+
+def device_count() -> int:
+    n = load_library().rt_device_count()
+    if n < 0:
+        _check(n)
+    return n
+
+
+def _device_pointer(obj) -> Optional[Tuple[int, int]]:
+    """(pointer, row stride in bytes) if `obj` lives in device memory, else None."""
+    if hasattr(obj, "data_ptr") and getattr(obj, "is_cuda", False):      # torch.Tensor, without importing torch
+        if obj.dim() == 1:
+            return int(obj.data_ptr()), int(obj.numel() * obj.element_size())
+        return int(obj.data_ptr()), int(obj.stride(0) * obj.element_size())
+    cai = getattr(obj, "__cuda_array_interface__", None)
+    if cai is not None:
+        shape = cai["shape"]
+        strides = cai.get("strides")
+        row = strides[0] if strides else int(np.prod(shape[1:]))
+        return int(cai["data"][0]), int(row)
+    return None
+
+
+class Engine:
+    """A batch of `n_streams` analyzers on one GPU (rt_engine handle)."""
+
+    def __init__(self, *, n_streams: int, block_samples: int, nperseg: int, window: np.ndarray, sample_rate: float,
+                 signal_threshold: Union[float, Sequence[float]], snr_threshold: float, probe_stride: int,
+                 min_cols: int, max_cols: int, max_records: int = 1 << 16, cuda_device: int = 0, fft_impl: int = FFT_AUTO):
+        self._lib = load_library()
+        self._h = ctypes.c_void_p()
+        win = np.ascontiguousarray(window, dtype=np.float64)
+        if win.shape != (nperseg,):
+            raise ValueError("window must have nperseg entries")
+        thr = np.ascontiguousarray(np.broadcast_to(np.asarray(signal_threshold, dtype=np.float64), (n_streams,)))
+        cfg = RtConfig(
+            abi_version=RT_ABI_VERSION, cuda_device=cuda_device, n_streams=n_streams, nperseg=nperseg,
+            block_samples=block_samples, sample_rate=float(sample_rate),
+            window=win.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+            signal_threshold=thr.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+            snr_threshold=float(snr_threshold), probe_stride=int(probe_stride), min_cols=int(min_cols),
+            max_cols=int(max_cols), max_records=int(max_records), fft_impl=int(fft_impl), reserved=0,
+        )
+        _check(self._lib.rt_engine_create(ctypes.byref(cfg), ctypes.byref(self._h)))
+        self.n_streams, self.nperseg, self.block_samples = n_streams, nperseg, block_samples
+        self.T = block_samples // nperseg
+        self.max_records = int(max_records)
+        self.cuda_device = cuda_device
+        self._out = np.empty(self.max_records, dtype=RECORD_DTYPE)
+        self._keepalive = None
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.rt_engine_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- data path ----------------------------------------------------------------------------
+    def _resolve(self, iq) -> Tuple[int, int, int]:
+        dev = _device_pointer(iq)
+        if dev is not None:
+            return dev[0], 1, dev[1]
+        arr = np.asarray(iq)
+        if arr.dtype != np.uint8:
+            raise TypeError("IQ blocks must be uint8 interleaved I,Q bytes")
+        if arr.ndim == 1:
+            arr = arr.reshape(1, -1)
+        if arr.shape != (self.n_streams, 2 * self.block_samples) or arr.strides[1] != 1:
+            raise ValueError(f"expected uint8 [{self.n_streams}, {2 * self.block_samples}], got {arr.shape}")
+        self._keepalive = arr
+        return int(arr.ctypes.data), 0, int(arr.strides[0])
+
+    def launch(self, iq) -> None:
+        """Enqueue one block for every stream (asynchronous)."""
+        ptr, on_dev, stride = self._resolve(iq)
+        _check(self._lib.rt_engine_launch(self._h, ctypes.c_void_p(ptr), on_dev, stride))
+
+    def fetch(self) -> np.ndarray:
+        """Wait for the last launch; candidate records sorted by (stream, fi, start)."""
+        n = ctypes.c_int32(0)
+        _check(self._lib.rt_engine_fetch(self._h, self._out.ctypes.data_as(ctypes.c_void_p), self.max_records, ctypes.byref(n)))
+        self._keepalive = None
+        return self._out[: n.value].copy()
+
+    def process(self, iq) -> np.ndarray:
+        ptr, on_dev, stride = self._resolve(iq)
+        n = ctypes.c_int32(0)
+        _check(self._lib.rt_engine_process(self._h, ctypes.c_void_p(ptr), on_dev, stride,
+                                           self._out.ctypes.data_as(ctypes.c_void_p), self.max_records, ctypes.byref(n)))
+        self._keepalive = None
+        return self._out[: n.value].copy()
+
+    def reset_stream(self, stream: int) -> None:
+        _check(self._lib.rt_engine_reset_stream(self._h, stream))
+
+    def set_stream(self, cuda_stream: int) -> None:
+        _check(self._lib.rt_engine_set_stream(self._h, ctypes.c_void_p(cuda_stream)))
+
+    # -- parity hooks / timing ------------------------------------------------------------------
+    def read_spectrogram(self, stream: int = 0) -> np.ndarray:
+        """float32 [T, nperseg] of the last launch (= scipy's Sxx transposed)."""
+        out = np.empty((self.T, self.nperseg), dtype=np.float32)
+        _check(self._lib.rt_engine_read_spectrogram(self._h, stream, out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def read_row_means(self, stream: int = 0) -> np.ndarray:
+        out = np.empty(self.nperseg, dtype=np.float32)
+        _check(self._lib.rt_engine_read_row_means(self._h, stream, out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def enable_timing(self, on: bool = True) -> None:
+        _check(self._lib.rt_engine_enable_timing(self._h, int(on)))
+
+    def timing(self, reset: bool = False) -> dict:
+        t = RtTiming()
+        _check(self._lib.rt_engine_get_timing(self._h, ctypes.byref(t), int(reset)))
+        return {k: getattr(t, k) for k, _ in RtTiming._fields_}

@@ -1,0 +1,175 @@
+"""CUDA path vs oracle vs reference fixtures, on the B200 (pytest -m gpu).  Everything goes through
+the C ABI (pyradiotracking_b200/engine.py -> librtb200.so)."""
+import datetime
+
+import numpy as np
+import pytest
+
+from oracle import restatement as R
+from oracle.cases import BY_NAME, CASES, sha256
+from pyradiotracking_b200 import engine as E
+from pyradiotracking_b200 import synth
+from pyradiotracking_b200.analyze import BatchAnalyzer, SignalAnalyzer
+from tests import golden_io, parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _impls(nperseg):
+    return [E.FFT_GENERIC, E.FFT_REG256] if nperseg == 256 else [E.FFT_GENERIC]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c.name)
+def test_case_matches_oracle_and_fixture(case):
+    g = golden_io.load(case.name)
+    kw = g.meta["analyzer"]
+    cap = case.capture()
+    assert sha256(cap) == g.meta["input_sha256"]
+    P = parity.oracle_params(kw)
+    for impl in _impls(kw["fft_nperseg"]):
+        ora = R.OracleAnalyzer(P)
+        ba = BatchAnalyzer(**parity.batch_kwargs(kw, fft_impl=impl))
+        try:
+            last = None
+            totals = dict(oracle=0, gpu=0, near_threshold_mismatch=0)
+            for b, gb in enumerate(g.blocks):
+                ts0 = parity.block_ts(g.t0, b, kw["sdr_callback_length"], kw["sample_rate"])
+                freqs, times, S, found, kept = ora.process_block(cap[b], ts0)
+                filtered, sigs, keys = ba.process_blocks(cap[b][None, :], [ts0])[0]
+                stats = parity.compare_block(P, S, last, found, sigs, keys)
+                parity.compare_spectrogram(P, S, ba.engine.read_spectrogram(0), ba.engine.read_row_means(0))
+                for k in totals:
+                    totals[k] += stats[k]
+                if stats["near_threshold_mismatch"] == 0:
+                    # identical candidate lists => the shadow filter must keep the same ones, and the
+                    # reference fixture must agree field by field
+                    assert [(s.ts, s.frequency) for s in filtered] == [(d.ts, d.frequency) for d in kept]
+                    assert [golden_io.us(s.ts - golden_io.EPOCH) for s in sigs] == gb.ts_us.tolist()
+                    assert [golden_io.us(s.duration) for s in sigs] == gb.dur_us.tolist()
+                    assert [s.frequency for s in sigs] == gb.freq.tolist()
+                    if len(sigs):
+                        got = np.array([[s.max, s.avg, s.std, s.noise, s.snr] for s in sigs])
+                        np.testing.assert_allclose(got, gb.stats, rtol=0, atol=parity.DB_ATOL)
+                    kept_ids = {id(s) for s in filtered}
+                    assert [id(s) in kept_ids for s in sigs] == gb.kept.tolist()
+                last = S
+            assert totals["gpu"] > 0
+            assert totals["near_threshold_mismatch"] <= max(2, totals["oracle"] // 50)
+        finally:
+            ba.close()
+
+
+class _Q:
+    def __init__(self):
+        self.items = []
+
+    def put(self, x):
+        self.items.append(x)
+
+
+class _V:
+    value = 0.0
+
+
+@pytest.mark.parametrize("name", ["c1_default_300k", "calib_hann_ragged", "tiny_T64"])
+def test_signal_analyzer_callback_matches_reference_queue(name):
+    """The drop-in class, driven like pyrtlsdr drives the reference: queue content == reference fixture."""
+    case = BY_NAME[name]
+    g = golden_io.load(name)
+    kw = dict(g.meta["analyzer"])
+    if isinstance(kw["fft_window"], list):
+        kw["fft_window"] = tuple(kw["fft_window"])
+    cap = case.capture()
+    q = _Q()
+    an = SignalAnalyzer(signal_queue=q, last_data_ts=_V(), **kw)
+    an.sdr = type("S", (), {"cancel_read_async": lambda self: None})()
+    bl = datetime.timedelta(seconds=kw["sdr_callback_length"] / kw["sample_rate"])
+    try:
+        for b, gb in enumerate(g.blocks):
+            an._now = lambda b=b: g.t0 + b * bl
+            before = len(q.items)
+            if b % 2:
+                an.process_samples(synth.bytes_to_iq(cap[b]), None)       # reference-compatible complex entry
+            else:
+                an.process_bytes(cap[b], None)                            # raw-byte entry
+            sigs = [m for m in q.items[before:] if isinstance(m, an.Signal)]
+            assert [golden_io.us(s.ts - golden_io.EPOCH) for s in sigs] == gb.ts_us[gb.kept].tolist()
+            assert [s.frequency for s in sigs] == gb.freq[gb.kept].tolist()
+            assert [golden_io.us(s.duration) for s in sigs] == gb.dur_us[gb.kept].tolist()
+            assert all(s.device == kw["device"] for s in sigs)
+            if len(sigs):
+                got = np.array([[s.max, s.avg, s.std, s.noise, s.snr] for s in sigs])
+                np.testing.assert_allclose(got, gb.stats[gb.kept], rtol=0, atol=parity.DB_ATOL)
+        states = [m for m in q.items if isinstance(m, an.StateMessage)]
+        assert [m.state.name for m in states][:2] == ["STARTED", "RUNNING"]
+    finally:
+        an.batch.close()
+
+
+def test_batch_of_streams_equals_single_streams():
+    """Streams are independent: a batch with per-stream calibration == each stream alone == oracle."""
+    w = synth.C1
+    n, nb = 5, 3
+    cal = [0.0, 1.5, -2.0, 3.25, 0.5]
+    cap = synth.make_batch(w, list(range(n)), nb)                   # [nb, n, 2N]
+    kw = BY_NAME["c1_default_300k"].analyzer_kwargs()
+    ba = BatchAnalyzer(**parity.batch_kwargs(kw, devices=[str(i) for i in range(n)], calibration=cal))
+    oras = [R.OracleAnalyzer(parity.oracle_params(dict(kw, device=str(i), calibration_db=cal[i]))) for i in range(n)]
+    t0 = datetime.datetime(2026, 2, 2, 2, 2, 2)
+    try:
+        lasts = [None] * n
+        for b in range(nb):
+            ts0 = [parity.block_ts(t0, b, w.block_samples, w.sample_rate)] * n
+            res = ba.process_blocks(cap[b], ts0)
+            for i in range(n):
+                freqs, times, S, found, kept = oras[i].process_block(cap[b, i], ts0[i])
+                stats = parity.compare_block(oras[i].P, S, lasts[i], found, res[i][1], res[i][2])
+                assert stats["near_threshold_mismatch"] == 0
+                assert [(s.ts, s.frequency, s.device) for s in res[i][0]] == [(d.ts, d.frequency, str(i)) for d in kept]
+                lasts[i] = S
+    finally:
+        ba.close()
+
+
+def test_device_resident_input_equals_host_input():
+    torch = pytest.importorskip("torch")
+    w = synth.C1
+    cap = synth.make_batch(w, [0, 1], 2)
+    kw = BY_NAME["c1_default_300k"].analyzer_kwargs()
+    a = BatchAnalyzer(**parity.batch_kwargs(kw, devices=["0", "1"], calibration=[0.0, 0.0]))
+    b = BatchAnalyzer(**parity.batch_kwargs(kw, devices=["0", "1"], calibration=[0.0, 0.0]))
+    try:
+        for blk in cap:
+            ra = a.engine.process(blk)
+            rb = b.engine.process(torch.from_numpy(blk).cuda())
+            assert ra.tobytes() == rb.tobytes() and len(ra) > 0
+    finally:
+        a.close()
+        b.close()
+
+
+def test_reset_stream_drops_the_carry():
+    case = BY_NAME["c1_default_300k"]
+    kw = case.analyzer_kwargs()
+    cap = case.capture()
+    ba = BatchAnalyzer(**parity.batch_kwargs(kw))
+    try:
+        ba.engine.process(cap[0][None, :])
+        with_carry = ba.engine.process(cap[1][None, :])
+        ba.reset_stream(0)
+        without = ba.engine.process(cap[1][None, :])
+        assert (with_carry["start"] < 0).any() and not (without["start"] < 0).any()
+    finally:
+        ba.close()
+
+
+def test_engine_rejects_bad_configuration():
+    win = np.ones(100)
+    with pytest.raises(E.EngineError):
+        E.Engine(n_streams=1, block_samples=1000, nperseg=100, window=win, sample_rate=1e5, signal_threshold=1e-9,
+                 snr_threshold=3.0, probe_stride=1, min_cols=0, max_cols=10)
+    with pytest.raises(E.EngineError):
+        E.Engine(n_streams=1, block_samples=300, nperseg=256, window=np.ones(256), sample_rate=1e5,
+                 signal_threshold=1e-9, snr_threshold=3.0, probe_stride=1, min_cols=0, max_cols=10)
+    with pytest.raises(IndexError):          # one-column block: analyze.py:354
+        BatchAnalyzer(**parity.batch_kwargs(dict(BY_NAME["c1_default_300k"].analyzer_kwargs(), sdr_callback_length=300)))

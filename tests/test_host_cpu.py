@@ -1,0 +1,138 @@
+"""CPU-only checks of the host layer: the C-ABI library builds, loads and exports what
+include/rt_engine.h declares; host float64 logic (plan, finaliser, shadow filter) vs the oracle;
+the register-FFT data flow emulated on the CPU vs numpy."""
+import datetime
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import restatement as R
+from pyradiotracking_b200 import build as B
+from pyradiotracking_b200 import engine as E
+from pyradiotracking_b200 import messages, synth
+from pyradiotracking_b200.analyze import BatchAnalyzer, DetectionPlan, iq_to_bytes, shadow_mask
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_loads_and_exports_header_symbols():
+    B.build()
+    lib = E.load_library()
+    hdr = open(os.path.join(ROOT, "include", "rt_engine.h")).read()
+    declared = set(re.findall(r"\b(rt_[a-z_]+)\s*\(", hdr))
+    assert declared == set(E.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.rt_abi_version() == E.RT_ABI_VERSION
+    assert E.RECORD_DTYPE.itemsize == 40
+
+
+def test_no_cpu_fallback_without_device():
+    torch = pytest.importorskip("torch")
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(E.EngineError):
+        E.Engine(n_streams=1, block_samples=300000, nperseg=256, window=np.ones(256), sample_rate=3e5,
+                 signal_threshold=1e-9, snr_threshold=3.0, probe_stride=9, min_cols=8, max_cols=49)
+
+
+@pytest.mark.parametrize("fs,n,N", [(300000, 256, 300000), (2400000, 256, 2400000), (256000, 256, 256000),
+                                    (20000000, 1024, 20000000), (20000000, 4096, 2000000), (300000, 256, 250123)])
+def test_plan_matches_scipy_axes_and_reference_stride(fs, n, N):
+    plan = DetectionPlan(fs, n, N, 0.008, 0.04)
+    f, t, _ = R.spectrogram(np.zeros(N, complex), fs, "boxcar", n)
+    assert np.array_equal(plan.freqs, f) and np.array_equal(plan.times, t)
+    assert plan.stride == max(1, int(0.008 / (t[1] - t[0])))
+    # every (start, end) that passes the float64 duration test also passes the coarse device gate
+    for start in (0, 5, -3):
+        for end in range(max(start, 0) + 1, min(plan.T, 600)):
+            _, dur = plan.duration(start, end)
+            if 0.008 <= dur <= 0.04:
+                cols = end - start + (1 if start < 0 else 0)
+                assert plan.min_cols <= cols <= plan.max_cols
+
+
+def test_stride_is_74_at_2p4_msps():
+    assert DetectionPlan(2400000, 256, 2400000, 0.008, 0.04).stride == 74        # SURVEY.md §7 hard part 3
+
+
+def test_shadow_mask_equals_reference_loop():
+    rng = np.random.default_rng(5)
+    t0 = datetime.datetime(2026, 1, 1, tzinfo=datetime.timezone.utc)
+    dets = [R.Detection(0, 0, 1, t0 + datetime.timedelta(microseconds=int(rng.integers(0, 200000))), 1.0,
+                        datetime.timedelta(microseconds=int(rng.integers(8000, 40000))), float(rng.integers(-90, -60)),
+                        0, 0, 0, 0) for _ in range(400)]
+    keep_ref = [d for d in dets if R.is_shadow_of(d, dets) is None]
+    ts = np.array([(d.ts - t0) // datetime.timedelta(microseconds=1) for d in dets])
+    du = np.array([d.duration // datetime.timedelta(microseconds=1) for d in dets])
+    mx = np.array([d.max for d in dets])
+    keep = [d for d, s in zip(dets, shadow_mask(ts, du, mx)) if not s]
+    assert keep == keep_ref and 0 < len(keep) < len(dets)
+
+
+def test_finaliser_reproduces_oracle_fields_from_exact_records():
+    """Feed the finaliser records built from the oracle's float64 spectrogram: every Signal field must
+    equal the oracle's (this isolates the host arithmetic from the device arithmetic)."""
+    w = synth.C1
+    cap = synth.make_stream(w, 2, 2)
+    P = R.Params.make(sample_rate=w.sample_rate, calibration_db=1.25)
+    ora = R.OracleAnalyzer(P)
+    ba = BatchAnalyzer(devices=["0"], calibration_db=[1.25], sample_rate=w.sample_rate, center_freq=w.center_freq,
+                       fft_nperseg=256, fft_window="hamming", signal_min_duration_ms=8, signal_max_duration_ms=40,
+                       signal_threshold_dbw=-90.0, snr_threshold_db=5.0)
+    t0 = datetime.datetime(2026, 4, 4, 4, 4, 4)
+    last = None
+    for b in range(2):
+        _, _, S, found, kept = ora.process_block(cap[b], t0)
+        rec = np.zeros(len(found), dtype=E.RECORD_DTYPE)
+        for i, d in enumerate(found):
+            data = np.concatenate((last[d.fi][d.start:], S[d.fi][:d.end])) if d.start < 0 else S[d.fi][d.start:d.end]
+            rec[i] = (0, d.fi, d.start, d.end, data.max(), S[d.fi].mean(), data.mean(), np.std(10 * np.log10(data)))
+        sigs, keys = ba.finalize(rec, [t0])[0]
+        assert keys == [d.key() for d in found]
+        for s, d in zip(sigs, found):
+            assert (s.ts, s.frequency, s.duration) == (d.ts, d.frequency, d.duration)
+            assert abs(s.max - d.max) < 1e-5 and abs(s.noise - d.noise) < 1e-5     # float32 max / row mean in the record
+            assert abs(s.avg - d.avg) < 1e-9 and abs(s.std - d.std) < 1e-9
+        assert [(s.ts, s.frequency) for s in ba.filter_shadow_signals(sigs)] == [(d.ts, d.frequency) for d in kept]
+        last = S
+    assert len(found) > 0
+
+
+def test_iq_to_bytes_round_trip_and_rejection():
+    u8 = synth.make_stream(synth.C1, 0, 1)[0][:4096]
+    assert np.array_equal(iq_to_bytes(synth.bytes_to_iq(u8)), u8)
+    with pytest.raises(ValueError):
+        iq_to_bytes(np.array([0.1234 + 0.5j]))
+
+
+def test_message_types_mirror_reference_surface():
+    s = messages.Signal("0", "2026-01-01T00:00:00+00:00", "150.1e6", 0.02, -60, -62, 1.0, -94, 30)
+    assert s.as_dict["Frequency"] == 150.1e6 and s.duration == datetime.timedelta(seconds=0.02)
+    assert messages.Signal.header == ["Device", "Time", "Frequency", "Duration", "max (dBW)", "avg (dBW)", "std (dB)", "noise (dBW)", "snr (dB)"]
+    m = messages.StateMessage("0", datetime.datetime.now(), 2)
+    assert m.state is messages.StateMessage.State.STARTED and m.as_list[2] == 2
+    assert abs(messages.from_dB(messages.dB(3.0)) - 3.0) < 1e-12
+
+
+def test_register_fft_dataflow_on_cpu(tmp_path):
+    """spectro_reg256's 16x16 decomposition, emulated with the same header on the host."""
+    exe = tmp_path / "hostcheck"
+    subprocess.run(["g++", "-O2", "-o", str(exe), os.path.join(ROOT, "tests", "csrc_host_check.cpp")], check=True)
+    rng = np.random.default_rng(3)
+    for trial in range(4):
+        raw = synth.make_stream(synth.C1, 40 + trial, 1)[0][trial * 512: trial * 512 + 512].copy()
+        if trial == 3:
+            raw = rng.integers(0, 256, 512).astype(np.uint8)           # full-scale bytes
+        win = R.resolve_window("hamming", 256).astype(np.float32)
+        out = subprocess.run([str(exe)], input=raw.tobytes() + win.tobytes(), capture_output=True, check=True).stdout
+        got = np.frombuffer(out, np.float32).astype(np.float64)
+        x = raw[0::2].astype(float) + 1j * raw[1::2].astype(float)
+        ref = np.abs(np.fft.fft((x - x.mean()) * win.astype(float))) ** 2
+        assert np.max(np.abs(got - ref) / ref.max()) < 1e-6
+        big = ref > 1e-3 * ref.max()
+        assert np.max(np.abs(got[big] - ref[big]) / ref[big]) < 2e-5
