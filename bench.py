@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=64, help="streams per GPU")
     ap.add_argument("--cpu-sample", type=int, default=8, help="stream-blocks timed for cpu_baseline")
+    ap.add_argument("--profile", action="store_true", help="device-resident region only (for runs under ncu)")
     return ap.parse_args()
 
 
@@ -268,13 +269,13 @@ def run_b200(args):
 
     t0 = datetime.datetime(2026, 1, 1)
     ts = [t0] * S
-    for i in range(2):
+    e2e_steps = 0 if args.profile else max(3, min(args.steps, 10))
+    for i in range(0 if args.profile else 2):
         ba.process_blocks(hnp[i % n_blk], ts)
     barrier()
     t_e2e = time.perf_counter()
     d2h = 0
     n_sig = 0
-    e2e_steps = max(3, min(args.steps, 10))
     for i in range(e2e_steps):
         res = ba.process_blocks(hnp[i % n_blk], ts)
         n_sig += sum(len(r[0]) for r in res)
@@ -297,9 +298,10 @@ def run_b200(args):
                        "l2": "inputs larger than L2 (307 MB per step, 2 alternating blocks)",
                        "records_per_step": n_rec},
             "clocks": clk,
-            "e2e": {"value": world * samples_per_step * e2e_steps / e2e_s / 1e6, "unit": UNIT,
-                    "h2d_bytes_per_step": S * w.block_bytes, "d2h_bytes_per_step": d2h // e2e_steps,
-                    "signals_per_step": n_sig / e2e_steps},
+            "e2e": None if args.profile else {
+                "value": world * samples_per_step * e2e_steps / e2e_s / 1e6, "unit": UNIT,
+                "h2d_bytes_per_step": S * w.block_bytes, "d2h_bytes_per_step": d2h // e2e_steps,
+                "signals_per_step": n_sig / e2e_steps},
             "gpu_launches": int(tim["kernels"]),
             "roofline": {"bound": "hbm", "kernel": "spectro_reg256", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": recorded_traffic(), "peak_source": peak_kind,
@@ -307,7 +309,7 @@ def run_b200(args):
                          "kernel_share_of_step": k_ms / (ms / args.steps),
                          "other_kernels_ms": {k: tim[k] / max(1, tim["launches"]) for k in ("rowmean_ms", "probe_ms", "extract_ms")}},
         }
-        if world == 1:
+        if world == 1 and not args.profile:
             v = cpu_port_single(args.cpu_sample)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"{args.cpu_sample} callback blocks (2.4 M samples each) of one stream, oracle port (numpy pocketfft + run extraction + shadow filter)"}

@@ -60,7 +60,7 @@ __device__ __forceinline__ int bin_pos(int fi) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// spectrogram, generic: any power-of-two nperseg in [8, 4096]; Stockham radix-2 in shared memory
+// spectrogram, generic: any power-of-two nperseg in [8, 4096]; Stockham radix-4 in shared memory
 // ---------------------------------------------------------------------------------------------
 struct SpectroArgs {
     const uint8_t* iq;
@@ -118,16 +118,37 @@ __global__ void __launch_bounds__(NT) spectro_generic(SpectroArgs a) {
         __syncthreads();
         float2* X = buf0;
         float2* Y = buf1;
-        int st = 1, lst = 0;
-        for (int ncur = n; ncur > 1; ncur >>= 1, st <<= 1, ++lst) {
-            const int m = ncur >> 1;
-            for (int b = tid; b < (n >> 1); b += NT) {
+        int st = 1, lst = 0, ncur = n;
+        // radix-4 Stockham passes (decimation in frequency, self-sorting)
+        for (; ncur >= 4; ncur >>= 2, st <<= 2, lst += 2) {
+            const int m = ncur >> 2;
+            for (int b = tid; b < (n >> 2); b += NT) {
                 const int p = b >> lst, q = b & (st - 1);
-                const float2 w = a.tw[p << lst];
-                const float2 u = X[q + st * p], v = X[q + st * (p + m)];
-                Y[q + st * 2 * p] = make_float2(u.x + v.x, u.y + v.y);
-                const float dr = u.x - v.x, di = u.y - v.y;
-                Y[q + st * (2 * p + 1)] = make_float2(dr * w.x - di * w.y, dr * w.y + di * w.x);
+                const float2 w1 = a.tw[p << lst], w2 = a.tw[(2 * p) << lst], w3 = a.tw[(3 * p) << lst];
+                const float2 x0 = X[q + st * p], x1 = X[q + st * (p + m)];
+                const float2 x2 = X[q + st * (p + 2 * m)], x3 = X[q + st * (p + 3 * m)];
+                const float apr = x0.x + x2.x, api = x0.y + x2.y, amr = x0.x - x2.x, ami = x0.y - x2.y;
+                const float bpr = x1.x + x3.x, bpi = x1.y + x3.y;
+                const float jr = -(x1.y - x3.y), ji = x1.x - x3.x;          // j * (x1 - x3)
+                float2* y = Y + q + st * 4 * p;
+                y[0] = make_float2(apr + bpr, api + bpi);
+                float tr = amr - jr, ti = ami - ji;
+                y[st] = make_float2(tr * w1.x - ti * w1.y, tr * w1.y + ti * w1.x);
+                tr = apr - bpr; ti = api - bpi;
+                y[2 * st] = make_float2(tr * w2.x - ti * w2.y, tr * w2.y + ti * w2.x);
+                tr = amr + jr; ti = ami + ji;
+                y[3 * st] = make_float2(tr * w3.x - ti * w3.y, tr * w3.y + ti * w3.x);
+            }
+            __syncthreads();
+            float2* t = X;
+            X = Y;
+            Y = t;
+        }
+        if (ncur == 2) {    // odd log2(n): one final radix-2 pass (twiddle-free)
+            for (int q = tid; q < st; q += NT) {
+                const float2 u = X[q], v = X[q + st];
+                Y[q] = make_float2(u.x + v.x, u.y + v.y);
+                Y[q + st] = make_float2(u.x - v.x, u.y - v.y);
             }
             __syncthreads();
             float2* t = X;

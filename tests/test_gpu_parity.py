@@ -37,7 +37,7 @@ def test_case_matches_oracle_and_fixture(case):
                 freqs, times, S, found, kept = ora.process_block(cap[b], ts0)
                 filtered, sigs, keys = ba.process_blocks(cap[b][None, :], [ts0])[0]
                 stats = parity.compare_block(P, S, last, found, sigs, keys)
-                parity.compare_spectrogram(P, S, ba.engine.read_spectrogram(0), ba.engine.read_row_means(0))
+                parity.compare_spectrogram(P, S, ba.engine.read_spectrogram(0), ba.engine.read_row_means(0), tag=f"{case.name}/impl{impl}/b{b}")
                 for k in totals:
                     totals[k] += stats[k]
                 if stats["near_threshold_mismatch"] == 0:
