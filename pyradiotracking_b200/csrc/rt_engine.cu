@@ -174,19 +174,64 @@ __global__ void __launch_bounds__(NT) spectro_generic(SpectroArgs a) {
 // ---------------------------------------------------------------------------------------------
 constexpr int R256_HW = 8;                 // half-warps (= segments in flight) per CTA
 constexpr int R256_THREADS = R256_HW * 16;
+constexpr int R256_STAGES = 4;             // TMA ring depth per half-warp
 constexpr int R256_RAW_STRIDE = 544;       // 512 B of IQ + 32 B pad: the two segments of a warp hit disjoint banks
 constexpr int R256_XROW = 36;              // floats per exchange row: 16 complex + 16 B pad (conflict-free LDS.128)
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 __global__ void __launch_bounds__(R256_THREADS, 4) spectro_reg256(SpectroArgs a) {
-    __shared__ __align__(16) unsigned char raw[R256_HW][R256_RAW_STRIDE];
+    // one warp = two segments in lock step (one per half-warp); per warp a ring of TMA-filled raw buffers
+    __shared__ __align__(16) unsigned char raw[R256_HW / 2][R256_STAGES][2][R256_RAW_STRIDE];
     __shared__ __align__(16) float xch[R256_HW][16 * R256_XROW];
+    __shared__ __align__(8) uint64_t full[R256_HW / 2][R256_STAGES];
 
     const int tid = threadIdx.x;
-    const int hw = tid >> 4, j = tid & 15;
-    const unsigned hmask = 0xffffu << (16 * (hw & 1));
+    const int warp = tid >> 5, lane = tid & 31, h = lane >> 4, j = lane & 15;
+    const int hw = tid >> 4;
     const int s = blockIdx.y;
     const int seg0 = blockIdx.x * a.chunk_segs;
     const int seg1 = min(a.T, seg0 + a.chunk_segs);
+    const uint8_t* base = a.iq + (size_t)s * a.stream_stride;
+    // iteration `it` of this warp covers segments seg0 + 8*it + 2*warp + {0, 1}
+    const int first = seg0 + 2 * warp;
+    const int n_it = (seg1 - first + R256_HW - 1) / R256_HW;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < R256_STAGES; ++st) mbar_init(&full[warp][st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+        for (int st = 0; st < R256_STAGES; ++st)
+            if (st < n_it) {
+                const int sg = first + R256_HW * st;
+                const int nv = min(2, seg1 - sg);
+                mbar_expect_tx(&full[warp][st], 512 * nv);
+                bulk_g2s(&raw[warp][st][0][0], base + (size_t)sg * 512, 512, &full[warp][st]);
+                if (nv == 2) bulk_g2s(&raw[warp][st][1][0], base + (size_t)(sg + 1) * 512, 512, &full[warp][st]);
+            }
+    }
 
     float wj[16], twr[16], twi[16], acc[16];
 #pragma unroll
@@ -197,12 +242,18 @@ __global__ void __launch_bounds__(R256_THREADS, 4) spectro_reg256(SpectroArgs a)
         twi[i] = t.y;
         acc[i] = 0.f;
     }
-    const uint8_t* base = a.iq + (size_t)s * a.stream_stride;
+    __syncwarp();                                   // barriers initialised before anyone polls them
 
-    for (int seg = seg0 + hw; seg < seg1; seg += R256_HW) {
-        const uint4* src = reinterpret_cast<const uint4*>(base + (size_t)seg * 512) + 2 * j;
-        const uint4 q0 = __ldg(src), q1 = __ldg(src + 1);
+    for (int it = 0; it < n_it; ++it) {
+        const int seg = first + R256_HW * it + h;
+        const bool valid = seg < seg1;              // odd tail: the upper half-warp idles through the last round
+        const int st = it % R256_STAGES;
+        const unsigned char* rb = &raw[warp][st][h][0];
+        while (!mbar_try_wait(&full[warp][st], (it / R256_STAGES) & 1)) {}
+
         // detrend: exact byte sums of I and Q over the 256 samples (bytes: I0 Q0 I1 Q1 per word)
+        const uint4 q0 = *reinterpret_cast<const uint4*>(rb + 16 * j);
+        const uint4 q1 = *reinterpret_cast<const uint4*>(rb + 256 + 16 * j);
         unsigned sI = 0, sQ = 0;
         sI = __dp4a(q0.x, 0x00010001u, sI); sQ = __dp4a(q0.x, 0x01000100u, sQ);
         sI = __dp4a(q0.y, 0x00010001u, sI); sQ = __dp4a(q0.y, 0x01000100u, sQ);
@@ -214,49 +265,58 @@ __global__ void __launch_bounds__(R256_THREADS, 4) spectro_reg256(SpectroArgs a)
         sI = __dp4a(q1.w, 0x00010001u, sI); sQ = __dp4a(q1.w, 0x01000100u, sQ);
         unsigned tot = sI | (sQ << 16);            // each total <= 255*256 < 2^16
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) tot += __shfl_xor_sync(hmask, tot, o, 16);
+        for (int o = 8; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);   // stays inside the half-warp
         // 32768 + mean: exact in fp32 (mean is a multiple of 2^-8, ulp(2^15) = 2^-8)
         const float cI = 32768.f + (float)(tot & 0xffffu) * 0.00390625f;
         const float cQ = 32768.f + (float)(tot >> 16) * 0.00390625f;
 
-        __syncwarp(hmask);                          // the previous segment's readers are done
-        *reinterpret_cast<uint4*>(&raw[hw][32 * j]) = q0;
-        *reinterpret_cast<uint4*>(&raw[hw][32 * j + 16]) = q1;
-        __syncwarp(hmask);
-
         rt::cf v[16];
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) {
-            const unsigned u = *reinterpret_cast<const unsigned short*>(&raw[hw][32 * n1 + 2 * j]);
+            const unsigned u = *reinterpret_cast<const unsigned short*>(rb + 32 * n1 + 2 * j);
             // byte -> float without I2F: 0x4700bb00 is 32768 + b
             const float fI = __uint_as_float(__byte_perm(u, 0x47000000u, 0x7604));
             const float fQ = __uint_as_float(__byte_perm(u, 0x47000000u, 0x7614));
             v[n1].re = (fI - cI) * wj[n1];
             v[n1].im = (fQ - cQ) * wj[n1];
         }
+        // this stage's bytes are in registers: refill it with the segments R256_STAGES rounds ahead
+        __syncwarp();
+        if (lane == 0 && it + R256_STAGES < n_it) {
+            const int sg = first + R256_HW * (it + R256_STAGES);
+            const int nv = min(2, seg1 - sg);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&full[warp][st], 512 * nv);
+            bulk_g2s(&raw[warp][st][0][0], base + (size_t)sg * 512, 512, &full[warp][st]);
+            if (nv == 2) bulk_g2s(&raw[warp][st][1][0], base + (size_t)(sg + 1) * 512, 512, &full[warp][st]);
+        }
+
         rt::dft16(v);                               // over n1 -> k1, for column n2 = j
 #pragma unroll
         for (int k1 = 1; k1 < 16; ++k1) v[k1] = rt::cmul(v[k1], twr[k1], twi[k1]);
 #pragma unroll
         for (int k1 = 0; k1 < 16; ++k1)
             *reinterpret_cast<float2*>(&xch[hw][k1 * R256_XROW + 2 * j]) = make_float2(v[k1].re, v[k1].im);
-        __syncwarp(hmask);
+        __syncwarp();
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             const float4 q = *reinterpret_cast<const float4*>(&xch[hw][j * R256_XROW + 4 * c]);
             v[2 * c] = rt::cf{q.x, q.y};
             v[2 * c + 1] = rt::cf{q.z, q.w};
         }
+        __syncwarp();                               // exchange rows consumed before the next round overwrites them
         rt::dft16(v);                               // over n2 -> k2, for k1 = j: bin = j + 16*k2
-        float p[16];
+        if (valid) {
+            float p[16];
 #pragma unroll
-        for (int k2 = 0; k2 < 16; ++k2) {
-            p[k2] = v[k2].re * v[k2].re + v[k2].im * v[k2].im;
-            acc[k2] += p[k2];
+            for (int k2 = 0; k2 < 16; ++k2) {
+                p[k2] = v[k2].re * v[k2].re + v[k2].im * v[k2].im;
+                acc[k2] += p[k2];
+            }
+            float4* dst = reinterpret_cast<float4*>(a.S + ((size_t)s * a.T + seg) * 256 + 16 * j);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dst[c] = make_float4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
         }
-        float4* dst = reinterpret_cast<float4*>(a.S + ((size_t)s * a.T + seg) * 256 + 16 * j);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) dst[c] = make_float4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
     }
 
     // chunk row sums: fixed-order reduction over the half-warps, written in FFT bin order
