@@ -25,7 +25,7 @@
 #include <vector>
 
 #include "../../include/rt_engine.h"
-#include "fft_regs.cuh"
+#include "fft_cpk.cuh"
 
 namespace {
 
@@ -52,11 +52,13 @@ __device__ __forceinline__ bool above(float p, float thr, float avg, float snr) 
     return !(p < thr) && !(__fdiv_rn(p, avg) < snr);
 }
 
-// bin -> position inside one stored spectrogram column.  The register kernel stores the 16 bins a
-// thread owns (k1 + 16*k2) contiguously, so its layout is the 16x16 transpose of FFT order.
+// bin -> position inside one stored spectrogram column.  In the register kernel thread j of a half-warp
+// ends up with bins j + 16*k2 (k2 = 0..15) and stores them as four float4 (k2 = 4c..4c+3); the layout
+// pos = 64*(k2 >> 2) + 4*j + (k2 & 3) makes each of those four store instructions lane-contiguous
+// (256 B per half-warp), i.e. fully coalesced.
 template <bool PERM>
 __device__ __forceinline__ int bin_pos(int fi) {
-    return PERM ? (((fi & 15) << 4) | (fi >> 4)) : fi;
+    return PERM ? (((fi >> 6) << 6) | ((fi & 15) << 2) | ((fi >> 4) & 3)) : fi;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -172,11 +174,18 @@ __global__ void __launch_bounds__(NT) spectro_generic(SpectroArgs a) {
 // spectrogram, nperseg == 256: 16 threads per segment, 16x16 Cooley-Tukey held in registers,
 // one shared-memory transpose between the two radix-16 passes
 // ---------------------------------------------------------------------------------------------
-constexpr int R256_HW = 8;                 // half-warps (= segments in flight) per CTA
-constexpr int R256_THREADS = R256_HW * 16;
-constexpr int R256_STAGES = 4;             // TMA ring depth per half-warp
+constexpr int R256_WARPS = 4;              // warps per CTA
+constexpr int R256_THREADS = R256_WARPS * 32;
+constexpr int R256_SEGS_PER_ROUND = 2 * R256_WARPS;   // a warp does 2 segments per round, one per half-warp
+constexpr int R256_STAGES = 4;             // TMA ring depth per warp (rounds in flight)
 constexpr int R256_RAW_STRIDE = 544;       // 512 B of IQ + 32 B pad: the two segments of a warp hit disjoint banks
 constexpr int R256_XROW = 36;              // floats per exchange row: 16 complex + 16 B pad (conflict-free LDS.128)
+constexpr int R256_XTILE = 16 * R256_XROW; // a half-warp's exchange tile
+constexpr int R256_CHUNK = 256;            // segments per CTA
+constexpr int R256_RAW_BYTES = R256_WARPS * R256_STAGES * 2 * R256_RAW_STRIDE;
+constexpr int R256_XCH_BYTES = 2 * R256_WARPS * R256_XTILE * 4;
+constexpr int R256_BAR_OFF = R256_RAW_BYTES + R256_XCH_BYTES;
+constexpr int R256_SMEM = R256_BAR_OFF + R256_WARPS * R256_STAGES * 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
@@ -200,11 +209,38 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// exact byte sums of I and Q over one 256-sample segment held in shared memory (bytes I0 Q0 I1 Q1 ...);
+// lane j of the half-warp adds 32 of the 512 bytes, the half-warp total comes back packed I | Q << 16
+__device__ __forceinline__ unsigned seg_byte_sums(const unsigned char* rb, int j) {
+    const uint4 q0 = *reinterpret_cast<const uint4*>(rb + 16 * j);
+    const uint4 q1 = *reinterpret_cast<const uint4*>(rb + 256 + 16 * j);
+    unsigned sI = 0, sQ = 0;
+    sI = __dp4a(q0.x, 0x00010001u, sI); sQ = __dp4a(q0.x, 0x01000100u, sQ);
+    sI = __dp4a(q0.y, 0x00010001u, sI); sQ = __dp4a(q0.y, 0x01000100u, sQ);
+    sI = __dp4a(q0.z, 0x00010001u, sI); sQ = __dp4a(q0.z, 0x01000100u, sQ);
+    sI = __dp4a(q0.w, 0x00010001u, sI); sQ = __dp4a(q0.w, 0x01000100u, sQ);
+    sI = __dp4a(q1.x, 0x00010001u, sI); sQ = __dp4a(q1.x, 0x01000100u, sQ);
+    sI = __dp4a(q1.y, 0x00010001u, sI); sQ = __dp4a(q1.y, 0x01000100u, sQ);
+    sI = __dp4a(q1.z, 0x00010001u, sI); sQ = __dp4a(q1.z, 0x01000100u, sQ);
+    sI = __dp4a(q1.w, 0x00010001u, sI); sQ = __dp4a(q1.w, 0x01000100u, sQ);
+    unsigned tot = sI | (sQ << 16);                // each total <= 255*256 < 2^16
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);   // stays inside the half-warp
+    return tot;
+}
+
+__device__ __forceinline__ rt::cpk detrend_const(unsigned tot) {
+    // (32768 + mean_I, 32768 + mean_Q): exact in fp32 (the mean of 256 bytes is a multiple of 2^-8 = ulp(2^15))
+    return rt::c_make(32768.f + (float)(tot & 0xffffu) * 0.00390625f, 32768.f + (float)(tot >> 16) * 0.00390625f);
+}
+
 __global__ void __launch_bounds__(R256_THREADS, 4) spectro_reg256(SpectroArgs a) {
-    // one warp = two segments in lock step (one per half-warp); per warp a ring of TMA-filled raw buffers
-    __shared__ __align__(16) unsigned char raw[R256_HW / 2][R256_STAGES][2][R256_RAW_STRIDE];
-    __shared__ __align__(16) float xch[R256_HW][16 * R256_XROW];
-    __shared__ __align__(8) uint64_t full[R256_HW / 2][R256_STAGES];
+    // 16 threads (a half-warp) hold one 256-point FFT as a 16x16 Cooley-Tukey in registers; every complex
+    // value is one packed register pair (fft_cpk.cuh).  A warp works on two consecutive segments per round.
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    unsigned char* raw = dyn_smem;                                                   // [warp][stage][half][544]
+    float* xch = reinterpret_cast<float*>(dyn_smem + R256_RAW_BYTES);                // [half-warp][16][R256_XROW]
+    uint64_t* full = reinterpret_cast<uint64_t*>(dyn_smem + R256_BAR_OFF);           // [warp][stage]
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31, h = lane >> 4, j = lane & 15;
@@ -213,124 +249,125 @@ __global__ void __launch_bounds__(R256_THREADS, 4) spectro_reg256(SpectroArgs a)
     const int seg0 = blockIdx.x * a.chunk_segs;
     const int seg1 = min(a.T, seg0 + a.chunk_segs);
     const uint8_t* base = a.iq + (size_t)s * a.stream_stride;
-    // iteration `it` of this warp covers segments seg0 + 8*it + 2*warp + {0, 1}
+    // round `it` of this warp covers segments first + 8*it + {0, 1}
     const int first = seg0 + 2 * warp;
-    const int n_it = (seg1 - first + R256_HW - 1) / R256_HW;
+    const int n_it = (seg1 - first + R256_SEGS_PER_ROUND - 1) / R256_SEGS_PER_ROUND;
+    unsigned char* wraw = raw + warp * (R256_STAGES * 2 * R256_RAW_STRIDE);
+    uint64_t* wfull = full + warp * R256_STAGES;
+    float* xt = xch + hw * R256_XTILE;              // [k1][n2] complex
 
     if (lane == 0) {
 #pragma unroll
-        for (int st = 0; st < R256_STAGES; ++st) mbar_init(&full[warp][st], 1);
+        for (int st = 0; st < R256_STAGES; ++st) mbar_init(&wfull[st], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #pragma unroll
         for (int st = 0; st < R256_STAGES; ++st)
             if (st < n_it) {
-                const int sg = first + R256_HW * st;
+                const int sg = first + R256_SEGS_PER_ROUND * st;
                 const int nv = min(2, seg1 - sg);
-                mbar_expect_tx(&full[warp][st], 512 * nv);
-                bulk_g2s(&raw[warp][st][0][0], base + (size_t)sg * 512, 512, &full[warp][st]);
-                if (nv == 2) bulk_g2s(&raw[warp][st][1][0], base + (size_t)(sg + 1) * 512, 512, &full[warp][st]);
+                mbar_expect_tx(&wfull[st], 512 * nv);
+                bulk_g2s(wraw + (st * 2) * R256_RAW_STRIDE, base + (size_t)sg * 512, 512, &wfull[st]);
+                if (nv == 2) bulk_g2s(wraw + (st * 2 + 1) * R256_RAW_STRIDE, base + (size_t)(sg + 1) * 512, 512, &wfull[st]);
             }
     }
 
-    float wj[16], twr[16], twi[16], acc[16];
+    // per-thread constants: window at samples 16*n1 + j, inter-pass twiddles W256^{j*k1} as (wr, (-wi, wi))
+    float wj[16], twr[16], acc[16];
+    unsigned long long twp[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        wj[i] = a.win[16 * i + j];                 // window at sample 16*n1 + j
-        const float2 t = a.tw[(j * i) & 255];      // W256^{j*k1}
+        wj[i] = a.win[16 * i + j];
+        const float2 t = a.tw[(j * i) & 255];
         twr[i] = t.x;
-        twi[i] = t.y;
+        twp[i] = rt::cpk_pair(-t.y, t.y);
         acc[i] = 0.f;
     }
     __syncwarp();                                   // barriers initialised before anyone polls them
 
+    // detrend constants of the first round (later rounds: computed one round ahead, off the critical path)
+    rt::cpk cm = rt::c_make(0.f, 0.f);
+    if (n_it > 0) {
+        while (!mbar_try_wait(&wfull[0], 0)) {}
+        cm = detrend_const(seg_byte_sums(wraw + h * R256_RAW_STRIDE, j));
+    }
+
     for (int it = 0; it < n_it; ++it) {
-        const int seg = first + R256_HW * it + h;
+        const int seg = first + R256_SEGS_PER_ROUND * it + h;
         const bool valid = seg < seg1;              // odd tail: the upper half-warp idles through the last round
         const int st = it % R256_STAGES;
-        const unsigned char* rb = &raw[warp][st][h][0];
-        while (!mbar_try_wait(&full[warp][st], (it / R256_STAGES) & 1)) {}
+        const unsigned char* rb = wraw + (st * 2 + h) * R256_RAW_STRIDE;
 
-        // detrend: exact byte sums of I and Q over the 256 samples (bytes: I0 Q0 I1 Q1 per word)
-        const uint4 q0 = *reinterpret_cast<const uint4*>(rb + 16 * j);
-        const uint4 q1 = *reinterpret_cast<const uint4*>(rb + 256 + 16 * j);
-        unsigned sI = 0, sQ = 0;
-        sI = __dp4a(q0.x, 0x00010001u, sI); sQ = __dp4a(q0.x, 0x01000100u, sQ);
-        sI = __dp4a(q0.y, 0x00010001u, sI); sQ = __dp4a(q0.y, 0x01000100u, sQ);
-        sI = __dp4a(q0.z, 0x00010001u, sI); sQ = __dp4a(q0.z, 0x01000100u, sQ);
-        sI = __dp4a(q0.w, 0x00010001u, sI); sQ = __dp4a(q0.w, 0x01000100u, sQ);
-        sI = __dp4a(q1.x, 0x00010001u, sI); sQ = __dp4a(q1.x, 0x01000100u, sQ);
-        sI = __dp4a(q1.y, 0x00010001u, sI); sQ = __dp4a(q1.y, 0x01000100u, sQ);
-        sI = __dp4a(q1.z, 0x00010001u, sI); sQ = __dp4a(q1.z, 0x01000100u, sQ);
-        sI = __dp4a(q1.w, 0x00010001u, sI); sQ = __dp4a(q1.w, 0x01000100u, sQ);
-        unsigned tot = sI | (sQ << 16);            // each total <= 255*256 < 2^16
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);   // stays inside the half-warp
-        // 32768 + mean: exact in fp32 (mean is a multiple of 2^-8, ulp(2^15) = 2^-8)
-        const float cI = 32768.f + (float)(tot & 0xffffu) * 0.00390625f;
-        const float cQ = 32768.f + (float)(tot >> 16) * 0.00390625f;
-
-        rt::cf v[16];
+        // uint8 -> float (0x4700bb00 is 32768 + b, no I2F), detrend (scipy detrend='constant'), window
+        rt::cpk v[16];
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) {
             const unsigned u = *reinterpret_cast<const unsigned short*>(rb + 32 * n1 + 2 * j);
-            // byte -> float without I2F: 0x4700bb00 is 32768 + b
-            const float fI = __uint_as_float(__byte_perm(u, 0x47000000u, 0x7604));
-            const float fQ = __uint_as_float(__byte_perm(u, 0x47000000u, 0x7614));
-            v[n1].re = (fI - cI) * wj[n1];
-            v[n1].im = (fQ - cQ) * wj[n1];
+            const rt::cpk f = rt::c_make(__uint_as_float(__byte_perm(u, 0x47000000u, 0x7604)),
+                                         __uint_as_float(__byte_perm(u, 0x47000000u, 0x7614)));
+            v[n1] = rt::c_scale(rt::c_sub(f, cm), wj[n1]);
         }
         // this stage's bytes are in registers: refill it with the segments R256_STAGES rounds ahead
         __syncwarp();
         if (lane == 0 && it + R256_STAGES < n_it) {
-            const int sg = first + R256_HW * (it + R256_STAGES);
+            const int sg = first + R256_SEGS_PER_ROUND * (it + R256_STAGES);
             const int nv = min(2, seg1 - sg);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&full[warp][st], 512 * nv);
-            bulk_g2s(&raw[warp][st][0][0], base + (size_t)sg * 512, 512, &full[warp][st]);
-            if (nv == 2) bulk_g2s(&raw[warp][st][1][0], base + (size_t)(sg + 1) * 512, 512, &full[warp][st]);
+            mbar_expect_tx(&wfull[st], 512 * nv);
+            bulk_g2s(wraw + (st * 2) * R256_RAW_STRIDE, base + (size_t)sg * 512, 512, &wfull[st]);
+            if (nv == 2) bulk_g2s(wraw + (st * 2 + 1) * R256_RAW_STRIDE, base + (size_t)(sg + 1) * 512, 512, &wfull[st]);
+        }
+        // byte sums of the NEXT round: the shuffle chain overlaps the butterflies below
+        unsigned tot = 0;
+        if (it + 1 < n_it) {
+            const int sn = (it + 1) % R256_STAGES;
+            while (!mbar_try_wait(&wfull[sn], ((it + 1) / R256_STAGES) & 1)) {}
+            tot = seg_byte_sums(wraw + (sn * 2 + h) * R256_RAW_STRIDE, j);
         }
 
-        rt::dft16(v);                               // over n1 -> k1, for column n2 = j
+        rt::cdft16(v);                              // over n1 -> k1, for column n2 = j
+        // inter-pass twiddles, then the 16x16 transpose through shared memory
+        *reinterpret_cast<unsigned long long*>(&xt[2 * j]) = v[0].v;
 #pragma unroll
-        for (int k1 = 1; k1 < 16; ++k1) v[k1] = rt::cmul(v[k1], twr[k1], twi[k1]);
-#pragma unroll
-        for (int k1 = 0; k1 < 16; ++k1)
-            *reinterpret_cast<float2*>(&xch[hw][k1 * R256_XROW + 2 * j]) = make_float2(v[k1].re, v[k1].im);
+        for (int k1 = 1; k1 < 16; ++k1) {
+            const rt::cpk t = rt::c_fma_swap_p(v[k1], twp[k1], rt::c_scale(v[k1], twr[k1]));
+            *reinterpret_cast<unsigned long long*>(&xt[k1 * R256_XROW + 2 * j]) = t.v;
+        }
+        cm = detrend_const(tot);
         __syncwarp();
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const float4 q = *reinterpret_cast<const float4*>(&xch[hw][j * R256_XROW + 4 * c]);
-            v[2 * c] = rt::cf{q.x, q.y};
-            v[2 * c + 1] = rt::cf{q.z, q.w};
+            const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(&xt[j * R256_XROW + 4 * c]);
+            v[2 * c].v = q.x;
+            v[2 * c + 1].v = q.y;
         }
-        __syncwarp();                               // exchange rows consumed before the next round overwrites them
-        rt::dft16(v);                               // over n2 -> k2, for k1 = j: bin = j + 16*k2
+        // (the tile is rewritten only after the next round's __syncwarp)
+        rt::cdft16(v);                              // over n2 -> k2, for k1 = j: bin = j + 16*k2
         if (valid) {
             float p[16];
 #pragma unroll
             for (int k2 = 0; k2 < 16; ++k2) {
-                p[k2] = v[k2].re * v[k2].re + v[k2].im * v[k2].im;
+                const float re = rt::c_re(v[k2]), im = rt::c_im(v[k2]);
+                p[k2] = re * re + im * im;
                 acc[k2] += p[k2];
             }
-            float4* dst = reinterpret_cast<float4*>(a.S + ((size_t)s * a.T + seg) * 256 + 16 * j);
+            float4* dst = reinterpret_cast<float4*>(a.S + ((size_t)s * a.T + seg) * 256 + 4 * j);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) dst[c] = make_float4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
+            for (int c = 0; c < 4; ++c) dst[16 * c] = make_float4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
         }
     }
 
-    // chunk row sums: fixed-order reduction over the half-warps, written in FFT bin order
+    // chunk row sums: fixed-order reduction over the half-warps, written in FFT bin order (fi = j + 16*k2)
     __syncthreads();
-    float* red = &xch[0][0];
+    float* red = xch;
 #pragma unroll
-    for (int k2 = 0; k2 < 16; ++k2) red[hw * 256 + 16 * j + k2] = acc[k2];
+    for (int k2 = 0; k2 < 16; ++k2) red[hw * 256 + 16 * k2 + j] = acc[k2];
     __syncthreads();
     float* pd = a.part + ((size_t)s * a.n_chunks + blockIdx.x) * 256;
     for (int fi = tid; fi < 256; fi += R256_THREADS) {
-        const int pos = bin_pos<true>(fi);
         float t = 0.f;
 #pragma unroll
-        for (int h = 0; h < R256_HW; ++h) t += red[h * 256 + pos];
+        for (int hh = 0; hh < 2 * R256_WARPS; ++hh) t += red[hh * 256 + fi];
         pd[fi] = t;
     }
 }
@@ -338,14 +375,20 @@ __global__ void __launch_bounds__(R256_THREADS, 4) spectro_reg256(SpectroArgs a)
 // ---------------------------------------------------------------------------------------------
 // row means (analyze.py:374-375), deterministic
 // ---------------------------------------------------------------------------------------------
-__global__ void row_mean_kernel(const float* part, float* avg, int n, int n_chunks, int T, int total) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // stream*n + fi
-    if (idx >= total) return;
-    const int s = idx / n, fi = idx - s * n;
+__global__ void row_mean_kernel(const float* part, float* avg, int n, int n_chunks, int T) {
+    const int fi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (fi >= n) return;
     const float* p = part + (size_t)s * n_chunks * n + fi;
-    double t = 0.0;
-    for (int c = 0; c < n_chunks; ++c) t += (double)p[(size_t)c * n];
-    avg[idx] = (float)(t / (double)T);
+    // fixed summation order (4 interleaved partial sums over the chunks), float64: run-to-run identical
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+    int c = 0;
+    for (; c + 4 <= n_chunks; c += 4) {
+        const float a0 = p[(size_t)c * n], a1 = p[(size_t)(c + 1) * n], a2 = p[(size_t)(c + 2) * n], a3 = p[(size_t)(c + 3) * n];
+        t0 += (double)a0; t1 += (double)a1; t2 += (double)a2; t3 += (double)a3;
+    }
+    for (; c < n_chunks; ++c) t0 += (double)p[(size_t)c * n];
+    avg[s * n + fi] = (float)(((t0 + t1) + (t2 + t3)) / (double)T);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -366,6 +409,7 @@ struct ScanArgs {
 };
 
 constexpr int PROBE_QUICK = 3;   // cells examined on each side before handing a probe hit to a warp
+constexpr int EX_W = 4;          // 32-cell windows an extraction warp examines per memory round trip
 
 template <bool PERM>
 __global__ void probe_kernel(ScanArgs a) {
@@ -377,7 +421,15 @@ __global__ void probe_kernel(ScanArgs a) {
     const int pos = bin_pos<PERM>(fi);
     const float* col = a.S + (size_t)s * a.T * a.n + pos;
     const float thr = a.thr[s], avg = a.avg[s * a.n + fi], snr = a.snr;
-    if (!above(col[(size_t)ti * a.n], thr, avg, snr)) return;
+    // the probe cell and its PROBE_QUICK neighbours on each side, loaded up front (one memory round trip)
+    float lo_c[PROBE_QUICK], hi_c[PROBE_QUICK];
+    const float c0 = col[(size_t)ti * a.n];
+#pragma unroll
+    for (int d = 1; d <= PROBE_QUICK; ++d) {
+        lo_c[d - 1] = (ti - d >= 0) ? col[(size_t)(ti - d) * a.n] : 0.f;
+        hi_c[d - 1] = (ti + d < a.T) ? col[(size_t)(ti + d) * a.n] : 0.f;
+    }
+    if (!above(c0, thr, avg, snr)) return;
 
     // Most hits are 1-2 cell noise runs that the duration gate rejects anyway: resolve those here.
     int lo = -1, hi = -1;             // nearest not-above cells, if found within PROBE_QUICK
@@ -385,13 +437,13 @@ __global__ void probe_kernel(ScanArgs a) {
     for (int d = 1; d <= PROBE_QUICK; ++d) {
         const int t = ti - d;
         if (t < 0) break;             // run reaches column 0: carry logic, leave it to the warp
-        if (!above(col[(size_t)t * a.n], thr, avg, snr)) { lo = t; break; }
+        if (!above(lo_c[d - 1], thr, avg, snr)) { lo = t; break; }
     }
 #pragma unroll
     for (int d = 1; d <= PROBE_QUICK; ++d) {
         const int t = ti + d;
         if (t >= a.T) return;         // run touches the block end: dropped (analyze.py:415-417)
-        if (!above(col[(size_t)t * a.n], thr, avg, snr)) { hi = t; break; }
+        if (!above(hi_c[d - 1], thr, avg, snr)) { hi = t; break; }
     }
     if (lo >= 0 && hi >= 0 && hi - lo < a.min_cols) return;   // window = [lo, hi): too short
     const int slot = atomicAdd(&a.counters[0], 1);
@@ -427,14 +479,21 @@ __global__ void extract_kernel(ScanArgs a) {
 
         // ---- backward: nearest not-above cell in [ti - stride, ti).  If there is none and the
         // previous probe column exists, that probe already owns this run (ti_skip, analyze.py:366).
+        // Every walk looks at EX_W * 32 cells per memory round trip.
         const int lo_lim = max(ti - a.stride, 0);
         int nb = -1;
-        for (int base = ti - 1; base >= lo_lim && nb < 0; base -= 32) {
-            const int t = base - lane;
-            const bool valid = t >= lo_lim;
-            const bool ab = valid ? above(col[(size_t)t * n], thr, avg, snr) : true;
-            const unsigned m = __ballot_sync(0xffffffffu, valid && !ab);
-            if (m) nb = base - (__ffs(m) - 1);
+        for (int base = ti - 1; base >= lo_lim && nb < 0; base -= 32 * EX_W) {
+            unsigned m[EX_W];
+#pragma unroll
+            for (int w = 0; w < EX_W; ++w) {
+                const int t = base - 32 * w - lane;
+                const bool valid = t >= lo_lim;
+                const float p = valid ? col[(size_t)t * n] : 0.f;
+                m[w] = __ballot_sync(0xffffffffu, valid && !above(p, thr, avg, snr));
+            }
+#pragma unroll
+            for (int w = 0; w < EX_W; ++w)
+                if (nb < 0 && m[w]) nb = base - 32 * w - (__ffs(m[w]) - 1);
         }
         int start;
         if (nb >= 0) {
@@ -449,12 +508,18 @@ __global__ void extract_kernel(ScanArgs a) {
             const int jmax = T - 2;                      // cells last[T-1] ... last[2]
             const int jcap = min(jmax, a.max_cols + 2);
             int jf = 0;
-            for (int base = 1; base <= jcap && jf == 0; base += 32) {
-                const int jj = base + lane;
-                const bool valid = jj <= jcap;
-                const bool ab = valid ? above(pcol[(size_t)(T - jj) * n], thr, avg, snr) : true;
-                const unsigned m = __ballot_sync(0xffffffffu, valid && !ab);
-                if (m) jf = base + (__ffs(m) - 1);
+            for (int base = 1; base <= jcap && jf == 0; base += 32 * EX_W) {
+                unsigned m[EX_W];
+#pragma unroll
+                for (int w = 0; w < EX_W; ++w) {
+                    const int jj = base + 32 * w + lane;
+                    const bool valid = jj <= jcap;
+                    const float p = valid ? pcol[(size_t)(T - jj) * n] : 0.f;
+                    m[w] = __ballot_sync(0xffffffffu, valid && !above(p, thr, avg, snr));
+                }
+#pragma unroll
+                for (int w = 0; w < EX_W; ++w)
+                    if (jf == 0 && m[w]) jf = base + 32 * w + (__ffs(m[w]) - 1);
             }
             if (jf > 0) start = -jf;
             else if (jcap == jmax) start = -(T - 1);     // ran into start_min
@@ -465,39 +530,51 @@ __global__ void extract_kernel(ScanArgs a) {
         int end = -1;
         const int span_cap = a.max_cols + 2;             // beyond this the duration test fails anyway
         bool too_long = false;
-        for (int base = ti + 1; base < T && end < 0; base += 32) {
+        for (int base = ti + 1; base < T && end < 0; base += 32 * EX_W) {
             if (base - start > span_cap) { too_long = true; break; }
-            const int t = base + lane;
-            const bool valid = t < T;
-            const bool ab = valid ? above(col[(size_t)t * n], thr, avg, snr) : true;
-            const unsigned m = __ballot_sync(0xffffffffu, valid && !ab);
-            if (m) end = base + (__ffs(m) - 1);
+            unsigned m[EX_W];
+#pragma unroll
+            for (int w = 0; w < EX_W; ++w) {
+                const int t = base + 32 * w + lane;
+                const bool valid = t < T;
+                const float p = valid ? col[(size_t)t * n] : 0.f;
+                m[w] = __ballot_sync(0xffffffffu, valid && !above(p, thr, avg, snr));
+            }
+#pragma unroll
+            for (int w = 0; w < EX_W; ++w)
+                if (end < 0 && m[w]) end = base + 32 * w + (__ffs(m[w]) - 1);
         }
         if (too_long || end < 0) continue;               // end == T: dropped, re-found from the next block
         const int cols = end - start + (start < 0 ? 1 : 0);
         if (cols < a.min_cols || cols > a.max_cols) continue;
 
-        // ---- statistics over data = [start, end) (analyze.py:436-447), float64 accumulation
+        // ---- statistics over data = [start, end) (analyze.py:436-447): one pass, float64 sums
         const int cnt = end - start;
         float mx = 0.f;
-        double sum = 0.0, sdb = 0.0;
-        for (int i = start + lane; i < end; i += 32) {
-            const float p = i < 0 ? pcol[(size_t)(T + i) * n] : col[(size_t)i * n];
-            mx = fmaxf(mx, p);
-            sum += (double)p;
-            sdb += 10.0 * log10((double)p);
+        double sum = 0.0, sdb = 0.0, sdb2 = 0.0;
+        for (int i0 = start + lane; i0 < end; i0 += 32 * EX_W) {
+            float pv[EX_W];
+#pragma unroll
+            for (int w = 0; w < EX_W; ++w) {
+                const int i = i0 + 32 * w;
+                pv[w] = i >= end ? -1.f : (i < 0 ? pcol[(size_t)(T + i) * n] : col[(size_t)i * n]);
+            }
+#pragma unroll
+            for (int w = 0; w < EX_W; ++w)
+                if (pv[w] >= 0.f) {
+                    mx = fmaxf(mx, pv[w]);
+                    sum += (double)pv[w];
+                    const double db = 10.0 * log10((double)pv[w]);
+                    sdb += db;
+                    sdb2 += db * db;
+                }
         }
         mx = warp_max(mx);
         sum = warp_sum(sum);
         sdb = warp_sum(sdb);
+        sdb2 = warp_sum(sdb2);
         const double mdb = sdb / cnt;
-        double ss = 0.0;
-        for (int i = start + lane; i < end; i += 32) {
-            const float p = i < 0 ? pcol[(size_t)(T + i) * n] : col[(size_t)i * n];
-            const double d = 10.0 * log10((double)p) - mdb;
-            ss += d * d;
-        }
-        ss = warp_sum(ss);
+        const double ss = fmax(sdb2 / cnt - mdb * mdb, 0.0) * cnt;
         if (lane == 0) {
             const int slot = atomicAdd(&a.counters[1], 1);
             if (slot < a.max_records) {
@@ -637,7 +714,7 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     e->n_probes = (e->T + cfg->probe_stride - 1) / cfg->probe_stride;
     if (cfg->fft_impl == RT_FFT_REG256 && n != 256) { delete e; return fail(RT_ERR_INVALID, "RT_FFT_REG256 needs nperseg == 256"); }
     e->reg256 = (n == 256) && (cfg->fft_impl != RT_FFT_GENERIC);
-    e->chunk_segs = e->reg256 ? 64 : 32;
+    e->chunk_segs = e->reg256 ? R256_CHUNK : 32;
     e->n_chunks = (e->T + e->chunk_segs - 1) / e->chunk_segs;
 
 #define CUE(call)                                                                                  \
@@ -691,6 +768,9 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     if (!e->reg256) {
         const size_t smem = (size_t)n * (2 * sizeof(float2) + sizeof(float)) + 16;
         CUE(cudaFuncSetAttribute(spectro_generic<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    } else {
+        CUE(cudaFuncSetAttribute(spectro_reg256, cudaFuncAttributeMaxDynamicSharedMemorySize, R256_SMEM));
+        CUE(cudaFuncSetAttribute(spectro_reg256, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     }
 #undef CUE
     *out = e;
@@ -775,7 +855,7 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     if (e->reg256 && !aligned) return fail(RT_ERR_INVALID, "register FFT path needs 16-byte aligned IQ and stream stride");
     dim3 grid(e->n_chunks, e->n_streams);
     if (use_reg) {
-        spectro_reg256<<<grid, R256_THREADS, 0, st>>>(sa);
+        spectro_reg256<<<grid, R256_THREADS, R256_SMEM, st>>>(sa);
     } else {
         const size_t smem = (size_t)e->n * (2 * sizeof(float2) + sizeof(float)) + 16;
         spectro_generic<256><<<grid, 256, smem, st>>>(sa);
@@ -783,8 +863,7 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     CU(cudaGetLastError());
     if (evs) CU(cudaEventRecord(evs->ev[1], st));
 
-    const int total = e->n_streams * e->n;
-    row_mean_kernel<<<(total + 127) / 128, 128, 0, st>>>(e->d_part, e->d_avg, e->n, e->n_chunks, e->T, total);
+    row_mean_kernel<<<dim3((e->n + 255) / 256, e->n_streams), 256, 0, st>>>(e->d_part, e->d_avg, e->n, e->n_chunks, e->T);
     CU(cudaGetLastError());
     if (evs) CU(cudaEventRecord(evs->ev[2], st));
 
@@ -799,8 +878,8 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     else probe_kernel<false><<<pgrid, 256, 0, st>>>(sc);
     CU(cudaGetLastError());
     if (evs) CU(cudaEventRecord(evs->ev[3], st));
-    if (use_reg) extract_kernel<true><<<296, 256, 0, st>>>(sc);
-    else extract_kernel<false><<<296, 256, 0, st>>>(sc);
+    if (use_reg) extract_kernel<true><<<148 * 8, 256, 0, st>>>(sc);
+    else extract_kernel<false><<<148 * 8, 256, 0, st>>>(sc);
     CU(cudaGetLastError());
     if (evs) CU(cudaEventRecord(evs->ev[4], st));
 

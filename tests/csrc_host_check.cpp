@@ -1,7 +1,7 @@
 // CPU emulation of the data flow of spectro_reg256 (pyradiotracking_b200/csrc/rt_engine.cu) for
-// ONE 256-sample segment, using the very same in-register FFT header.  The build container has
-// no GPU; this lets `pytest -m "not gpu"` check the index algebra (16x16 Cooley-Tukey, twiddles,
-// byte->float trick, stored bin permutation) against numpy.
+// ONE 256-sample segment, using the very same packed-complex FFT header (host flavour).  The build
+// container has no GPU; this lets `pytest -m "not gpu"` check the index algebra (16x16 Cooley-Tukey,
+// twiddles, byte->float trick, stored bin permutation) against numpy.
 //   stdin : 512 raw bytes, then 256 float32 window values
 //   stdout: 256 float32 power values in FFT bin order
 #include <cmath>
@@ -10,7 +10,7 @@
 #include <cstring>
 #include <vector>
 
-#include "../pyradiotracking_b200/csrc/fft_regs.cuh"
+#include "../pyradiotracking_b200/csrc/fft_cpk.cuh"
 
 static float magic_byte(unsigned b) {          // 0x4700bb00 == 32768 + b
     uint32_t u = 0x47000000u | (b << 8);
@@ -26,28 +26,27 @@ int main() {
     if (fread(win.data(), 4, 256, stdin) != 256) return 1;
     unsigned sI = 0, sQ = 0;
     for (int i = 0; i < 256; ++i) { sI += raw[2 * i]; sQ += raw[2 * i + 1]; }
-    const float cI = 32768.f + (float)sI * 0.00390625f, cQ = 32768.f + (float)sQ * 0.00390625f;
-    static float xch[16][36];
+    const rt::cpk c = rt::c_make(32768.f + (float)sI * 0.00390625f, 32768.f + (float)sQ * 0.00390625f);
+    static rt::cpk xch[16][16];
     float out_pos[256];
     for (int j = 0; j < 16; ++j) {              // "thread" j: column n2 = j
-        rt::cf v[16];
+        rt::cpk v[16];
         for (int n1 = 0; n1 < 16; ++n1) {
             const int smp = 16 * n1 + j;
-            v[n1].re = (magic_byte(raw[2 * smp]) - cI) * win[smp];
-            v[n1].im = (magic_byte(raw[2 * smp + 1]) - cQ) * win[smp];
+            v[n1] = rt::c_scale(rt::c_sub(rt::c_make(magic_byte(raw[2 * smp]), magic_byte(raw[2 * smp + 1])), c), win[smp]);
         }
-        rt::dft16(v);
+        rt::cdft16(v);
         for (int k1 = 1; k1 < 16; ++k1) {
             const double ang = -2.0 * M_PI * (double)((j * k1) & 255) / 256.0;
-            v[k1] = rt::cmul(v[k1], (float)std::cos(ang), (float)std::sin(ang));
+            v[k1] = rt::c_mul(v[k1], (float)std::cos(ang), (float)std::sin(ang));
         }
-        for (int k1 = 0; k1 < 16; ++k1) { xch[k1][2 * j] = v[k1].re; xch[k1][2 * j + 1] = v[k1].im; }
+        for (int k1 = 0; k1 < 16; ++k1) xch[k1][j] = v[k1];
     }
     for (int j = 0; j < 16; ++j) {              // "thread" j: row k1 = j
-        rt::cf v[16];
-        for (int c = 0; c < 16; ++c) v[c] = rt::cf{xch[j][2 * c], xch[j][2 * c + 1]};
-        rt::dft16(v);
-        for (int k2 = 0; k2 < 16; ++k2) out_pos[16 * j + k2] = v[k2].re * v[k2].re + v[k2].im * v[k2].im;
+        rt::cpk v[16];
+        for (int c2 = 0; c2 < 16; ++c2) v[c2] = xch[j][c2];
+        rt::cdft16(v);
+        for (int k2 = 0; k2 < 16; ++k2) out_pos[16 * j + k2] = rt::c_re(v[k2]) * rt::c_re(v[k2]) + rt::c_im(v[k2]) * rt::c_im(v[k2]);
     }
     float out[256];
     for (int fi = 0; fi < 256; ++fi) out[fi] = out_pos[((fi & 15) << 4) | (fi >> 4)];
