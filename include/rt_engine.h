@@ -118,9 +118,10 @@ int rt_engine_reset_stream(rt_engine *e, int32_t stream);
 int rt_engine_process(rt_engine *e, const uint8_t *iq, int32_t iq_on_device, size_t stream_stride_bytes,
                       rt_record *out, int32_t max_out, int32_t *n_out);
 
-/* The same in two halves: enqueue only (asynchronous) ... */
+/* The same in two halves: enqueue only (asynchronous; a host `iq` must stay valid until the fetch) ... */
 int rt_engine_launch(rt_engine *e, const uint8_t *iq, int32_t iq_on_device, size_t stream_stride_bytes);
-/* ... then wait, copy back and sort the records of the last launch. */
+/* ... then wait for the OLDEST unfetched launch, copy back and sort its records.  Two launches may be in
+ * flight (launch i+1 can be queued before fetch i); a third launch drops the oldest unfetched result. */
 int rt_engine_fetch(rt_engine *e, rt_record *out, int32_t max_out, int32_t *n_out);
 
 /* Spectrogram geometry: *T = block_samples / nperseg columns per block. */

@@ -20,7 +20,7 @@ import multiprocessing
 import signal as _signal
 import sys
 import time
-from typing import List, Optional, Sequence, Tuple
+from typing import List, NamedTuple, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -85,6 +85,30 @@ def _us(td: datetime.timedelta) -> int:
     return (td.days * 86400 + td.seconds) * 1_000_000 + td.microseconds
 
 
+def timedelta_us(seconds: np.ndarray) -> np.ndarray:
+    """int64 microseconds of `datetime.timedelta(seconds=x)` for float64 x, vectorised: CPython splits x with
+    modf and rounds the fractional microseconds half-to-even."""
+    frac, whole = np.modf(np.asarray(seconds, dtype=np.float64))
+    return whole.astype(np.int64) * 1_000_000 + np.rint(frac * 1e6).astype(np.int64)
+
+
+class Finalized(NamedTuple):
+    """Column view of the signals of one engine call (rows sorted by stream, bin, start)."""
+    stream: np.ndarray
+    fi: np.ndarray
+    start: np.ndarray
+    end: np.ndarray
+    ts_off_us: np.ndarray       # microseconds from the stream's ts_start (analyze.py:434)
+    dur_us: np.ndarray
+    frequency: np.ndarray
+    max: np.ndarray
+    avg: np.ndarray
+    std: np.ndarray
+    noise: np.ndarray
+    snr: np.ndarray
+    shadow: np.ndarray          # True: dropped by filter_shadow_signals
+
+
 def shadow_mask(ts_us: np.ndarray, dur_us: np.ndarray, max_dbw: np.ndarray) -> np.ndarray:
     """True where a signal is a shadow (analyze.py:283-313): some signal of the same list overlaps
     it in time (closed intervals, microsecond datetimes) and is strictly louder.  No frequency term."""
@@ -129,6 +153,7 @@ class BatchAnalyzer:
         self.max_records = max_records
         self.fft_impl = fft_impl
         self._engine: Optional[_engine.Engine] = None
+        self.last_record_count = 0          # candidate records copied back by the last collect()
         self.Signal, self.StateMessage = message_types()
 
     # the engine is created on first use: after a fork, inside the analyzer process
@@ -154,28 +179,64 @@ class BatchAnalyzer:
         self.engine.reset_stream(stream)
 
     # -- finaliser: records -> Signal objects ----------------------------------------------------
+    def finalize_arrays(self, records: np.ndarray) -> "Finalized":
+        """Vectorised analyze.py:419-450 for the candidate records of one engine call (sorted by stream, bin,
+        start): exact float64 duration test, timestamps / durations rounded to microseconds exactly like
+        `datetime.timedelta(seconds=float)`, dB statistics, and the per-stream shadow mask (analyze.py:283-328)."""
+        plan = self.plan
+        times = plan.times
+        start = records["start"].astype(np.int64)
+        end = records["end"].astype(np.int64)
+        neg = start < 0
+        start_dt = np.where(neg, -times[np.where(neg, -start, 0)], times[np.where(neg, 0, start)])   # :420-425
+        duration_s = times[end] - start_dt                                                             # :427
+        ok = ~(duration_s < self.signal_min_duration) & ~(duration_s > self.signal_max_duration)       # :429-433
+        r = records[ok]
+        start_dt, duration_s = start_dt[ok], duration_s[ok]
+        stream = r["stream"].astype(np.int64)
+        cal = np.asarray(self.calibration_db, dtype=np.float64)[stream]
+        mean = r["mean_lin"].astype(np.float64)
+        row = r["row_mean"].astype(np.float64)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            fin = Finalized(
+                stream=stream, fi=r["fi"].astype(np.int64), start=r["start"].astype(np.int64), end=r["end"].astype(np.int64),
+                ts_off_us=timedelta_us(start_dt), dur_us=timedelta_us(duration_s),
+                frequency=plan.freqs[r["fi"]] + self.center_freq,
+                max=10 * np.log10(r["max_lin"].astype(np.float64)) - cal, avg=10 * np.log10(mean) - cal,
+                std=r["std_db"].astype(np.float64), noise=10 * np.log10(row), snr=10 * np.log10(mean / row),
+                shadow=np.zeros(len(r), dtype=bool))
+        # shadow filter per stream (signals of one callback share ts_start, so offsets are enough)
+        bounds = np.searchsorted(fin.stream, np.arange(self.n_streams + 1))
+        for s in range(self.n_streams):
+            lo, hi = bounds[s], bounds[s + 1]
+            if hi - lo > 1:
+                fin.shadow[lo:hi] = shadow_mask(fin.ts_off_us[lo:hi], fin.dur_us[lo:hi], fin.max[lo:hi])
+        return fin
+
+    def build_signals(self, fin: "Finalized", ts_start: Sequence[datetime.datetime], keep: Optional[np.ndarray] = None):
+        """Signal objects per stream, in the reference's emission order (bin, then time), for the rows of
+        `fin` selected by `keep` (default: all)."""
+        out = [[] for _ in range(self.n_streams)]
+        Signal, devices = self.Signal, self.devices
+        idx = np.arange(len(fin.stream)) if keep is None else np.nonzero(keep)[0]
+        td = datetime.timedelta
+        for i, s, off, dur, f, mx, av, sd, no, sn in zip(
+                idx.tolist(), fin.stream[idx].tolist(), fin.ts_off_us[idx].tolist(), fin.dur_us[idx].tolist(),
+                fin.frequency[idx].tolist(), fin.max[idx].tolist(), fin.avg[idx].tolist(), fin.std[idx].tolist(),
+                fin.noise[idx].tolist(), fin.snr[idx].tolist()):
+            ts = (ts_start[s] + td(microseconds=off)).astimezone(UTC)
+            out[s].append(Signal(devices[s], ts, f, td(microseconds=dur), mx, av, sd, no, sn))
+        return out
+
     def finalize(self, records: np.ndarray, ts_start: Sequence[datetime.datetime]):
         """-> per stream `(signals, keys)`: the reference's `extract_signals` output (analyze.py:419-450)
         in its order (bin, then time) and the integer `(fi, start, end)` of each."""
-        plan = self.plan
-        out = [([], []) for _ in range(self.n_streams)]
-        Signal = self.Signal
-        for r in records:
-            s, fi, start, end = int(r["stream"]), int(r["fi"]), int(r["start"]), int(r["end"])
-            start_dt, duration_s = plan.duration(start, end)
-            if duration_s < self.signal_min_duration or duration_s > self.signal_max_duration:
-                continue
-            cal = self.calibration_db[s]
-            ts = ts_start[s] + datetime.timedelta(seconds=start_dt)
-            avg = float(r["mean_lin"])
-            freq_avg = float(r["row_mean"])
-            sig = Signal(
-                self.devices[s], ts.astimezone(UTC), plan.freqs[fi] + self.center_freq, datetime.timedelta(seconds=duration_s),
-                10 * np.log10(float(r["max_lin"])) - cal, 10 * np.log10(avg) - cal, float(r["std_db"]),
-                10 * np.log10(freq_avg), 10 * np.log10(avg / freq_avg))
-            out[s][0].append(sig)
-            out[s][1].append((fi, start, end))
-        return out
+        fin = self.finalize_arrays(records)
+        sigs = self.build_signals(fin, ts_start)
+        keys = [[] for _ in range(self.n_streams)]
+        for s, k in zip(fin.stream.tolist(), zip(fin.fi.tolist(), fin.start.tolist(), fin.end.tolist())):
+            keys[s].append(k)
+        return list(zip(sigs, keys))
 
     @staticmethod
     def filter_shadow_signals(signals: list) -> list:
@@ -190,12 +251,37 @@ class BatchAnalyzer:
         return [s for s, sh in zip(signals, shadow) if not sh]
 
     # -- one callback for every stream --------------------------------------------------------------
+    def submit(self, iq) -> None:
+        """Enqueue one block of every stream (H2D copy if `iq` is a host array, then the kernels); returns at once.
+        Up to two submissions may be in flight; results come back in order from `collect`."""
+        self.engine.launch(iq)
+
+    def collect(self, ts_start: Sequence[datetime.datetime], with_all: bool = False):
+        """Wait for the oldest submission.  -> per stream `(filtered_signals, n_before_filter)`, or with
+        `with_all` `(filtered_signals, all_signals, keys)` like `process_blocks`."""
+        records = self.engine.fetch()
+        self.last_record_count = len(records)
+        fin = self.finalize_arrays(records)
+        if not with_all:
+            kept = self.build_signals(fin, ts_start, ~fin.shadow)
+            counts = np.bincount(fin.stream, minlength=self.n_streams)
+            return [(kept[s], int(counts[s])) for s in range(self.n_streams)]
+        sigs = self.build_signals(fin, ts_start)
+        keys = [[] for _ in range(self.n_streams)]
+        kept = [[] for _ in range(self.n_streams)]
+        pos = [0] * self.n_streams
+        for s, sh, k in zip(fin.stream.tolist(), fin.shadow.tolist(), zip(fin.fi.tolist(), fin.start.tolist(), fin.end.tolist())):
+            keys[s].append(k)
+            if not sh:
+                kept[s].append(sigs[s][pos[s]])      # the very objects of `sigs`, in order
+            pos[s] += 1
+        return [(kept[s], sigs[s], keys[s]) for s in range(self.n_streams)]
+
     def process_blocks(self, iq, ts_start: Sequence[datetime.datetime]):
         """`iq`: uint8 `[n_streams, 2*block_samples]` on the host, or a CUDA tensor of that shape.
         -> per stream `(filtered_signals, all_signals, keys)`."""
-        records = self.engine.process(iq)
-        per_stream = self.finalize(records, ts_start)
-        return [(self.filter_shadow_signals(sigs), sigs, keys) for sigs, keys in per_stream]
+        self.submit(iq)
+        return self.collect(ts_start, with_all=True)
 
 
 def iq_to_bytes(buffer: np.ndarray) -> np.ndarray:

@@ -30,6 +30,7 @@
 namespace {
 
 thread_local std::string g_err;
+constexpr int RT_SLOTS = 2;     // launches that may be in flight before rt_engine_fetch
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -622,8 +623,12 @@ struct rt_engine {
     uint8_t* d_stage = nullptr;
     size_t stage_stride = 0;
     uint2* d_work = nullptr;
-    int* d_counters = nullptr;
-    rt_record* d_rec = nullptr;
+    // results ring: up to RT_SLOTS launches may be in flight before their records are fetched
+    int* d_counters = nullptr;              // [slot][2]
+    rt_record* d_rec[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
+    unsigned long long launch_seq = 0, fetch_seq = 0;
     rt_record* h_rec = nullptr;     // pinned
     int* h_counters = nullptr;      // pinned
     float* d_tmp = nullptr;         // parity hook scratch
@@ -661,7 +666,9 @@ void free_engine(rt_engine* e) {
         for (auto& ev : s.ev) cudaEventDestroy(ev);
     cudaFree(e->d_win); cudaFree(e->d_tw); cudaFree(e->d_S[0]); cudaFree(e->d_S[1]);
     cudaFree(e->d_part); cudaFree(e->d_avg); cudaFree(e->d_thr); cudaFree(e->d_hasprev);
-    cudaFree(e->d_stage); cudaFree(e->d_work); cudaFree(e->d_counters); cudaFree(e->d_rec); cudaFree(e->d_tmp);
+    cudaFree(e->d_stage); cudaFree(e->d_work); cudaFree(e->d_counters); cudaFree(e->d_rec[0]); cudaFree(e->d_rec[1]); cudaFree(e->d_tmp);
+    for (auto& ev : e->done) if (ev) cudaEventDestroy(ev);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->h_rec) cudaFreeHost(e->h_rec);
     if (e->h_counters) cudaFreeHost(e->h_counters);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
@@ -756,8 +763,12 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     CUE(cudaMalloc(&e->d_thr, e->n_streams * sizeof(float)));
     CUE(cudaMalloc(&e->d_hasprev, e->n_streams * sizeof(int)));
     CUE(cudaMalloc(&e->d_work, max_work * sizeof(uint2)));
-    CUE(cudaMalloc(&e->d_counters, 2 * sizeof(int)));
-    CUE(cudaMalloc(&e->d_rec, (size_t)cfg->max_records * sizeof(rt_record)));
+    CUE(cudaMalloc(&e->d_counters, 2 * RT_SLOTS * sizeof(int)));
+    for (int k = 0; k < RT_SLOTS; ++k) {
+        CUE(cudaMalloc(&e->d_rec[k], (size_t)cfg->max_records * sizeof(rt_record)));
+        CUE(cudaEventCreateWithFlags(&e->done[k], cudaEventDisableTiming));
+    }
+    CUE(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
     CUE(cudaMallocHost(&e->h_rec, (size_t)cfg->max_records * sizeof(rt_record)));
     CUE(cudaMallocHost(&e->h_counters, 2 * sizeof(int)));
     CUE(cudaMemcpy(e->d_win, hwin.data(), n * sizeof(float), cudaMemcpyHostToDevice));
@@ -829,7 +840,10 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
         CU(cudaMemcpyAsync(e->d_hasprev, e->h_hasprev.data(), e->n_streams * sizeof(int), cudaMemcpyHostToDevice, st));
         e->hasprev_dirty = false;
     }
-    CU(cudaMemsetAsync(e->d_counters, 0, 2 * sizeof(int), st));
+    const int slot = (int)(e->launch_seq % RT_SLOTS);
+    if (e->launch_seq - e->fetch_seq == RT_SLOTS) e->fetch_seq++;      // ring full: the oldest unfetched result is dropped
+    int* d_cnt = e->d_counters + 2 * slot;
+    CU(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), st));
 
     rt_engine::EvSet* evs = nullptr;
     if (e->timing) {
@@ -872,7 +886,7 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     sc.snr = (float)e->cfg.snr_threshold;
     sc.n = e->n; sc.T = e->T; sc.stride = e->cfg.probe_stride; sc.n_probes = e->n_probes;
     sc.min_cols = e->cfg.min_cols; sc.max_cols = e->cfg.max_cols;
-    sc.work = e->d_work; sc.counters = e->d_counters; sc.rec = e->d_rec; sc.max_records = e->cfg.max_records;
+    sc.work = e->d_work; sc.counters = d_cnt; sc.rec = e->d_rec[slot]; sc.max_records = e->cfg.max_records;
     dim3 pgrid((e->n_probes * e->n + 255) / 256, e->n_streams);
     if (use_reg) probe_kernel<true><<<pgrid, 256, 0, st>>>(sc);
     else probe_kernel<false><<<pgrid, 256, 0, st>>>(sc);
@@ -883,6 +897,8 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     CU(cudaGetLastError());
     if (evs) CU(cudaEventRecord(evs->ev[4], st));
 
+    CU(cudaEventRecord(e->done[slot], st));
+    e->launch_seq++;
     e->cur = next;
     for (auto& h : e->h_hasprev)
         if (!h) { h = 1; e->hasprev_dirty = true; }
@@ -894,17 +910,21 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
 
 int rt_engine_fetch(rt_engine* e, rt_record* out, int32_t max_out, int32_t* n_out) {
     if (!e || !n_out) return fail(RT_ERR_INVALID, "null argument");
-    if (!e->launched) return fail(RT_ERR_STATE, "rt_engine_fetch without rt_engine_launch");
+    if (e->fetch_seq == e->launch_seq) return fail(RT_ERR_STATE, "rt_engine_fetch without an unfetched rt_engine_launch");
     CU(cudaSetDevice(e->dev));
-    CU(cudaMemcpyAsync(e->h_counters, e->d_counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
+    const int slot = (int)(e->fetch_seq % RT_SLOTS);
+    e->fetch_seq++;
+    // copy on a side stream that only waits for THIS launch, so a later launch already queued does not delay it
+    CU(cudaStreamWaitEvent(e->copy_stream, e->done[slot], 0));
+    CU(cudaMemcpyAsync(e->h_counters, e->d_counters + 2 * slot, 2 * sizeof(int), cudaMemcpyDeviceToHost, e->copy_stream));
+    CU(cudaStreamSynchronize(e->copy_stream));
     const int nrec = e->h_counters[1];
     *n_out = nrec;
     if (nrec > e->cfg.max_records) return fail(RT_ERR_OVERFLOW, "more candidate records than rt_config.max_records");
     if (nrec > max_out || (nrec > 0 && !out)) return fail(RT_ERR_OVERFLOW, "output buffer smaller than the number of records");
     if (nrec > 0) {
-        CU(cudaMemcpyAsync(e->h_rec, e->d_rec, (size_t)nrec * sizeof(rt_record), cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaStreamSynchronize(e->stream));
+        CU(cudaMemcpyAsync(e->h_rec, e->d_rec[slot], (size_t)nrec * sizeof(rt_record), cudaMemcpyDeviceToHost, e->copy_stream));
+        CU(cudaStreamSynchronize(e->copy_stream));
         std::sort(e->h_rec, e->h_rec + nrec, [](const rt_record& x, const rt_record& y) {
             if (x.stream != y.stream) return x.stream < y.stream;
             if (x.fi != y.fi) return x.fi < y.fi;

@@ -146,7 +146,7 @@ class Engine:
         self.max_records = int(max_records)
         self.cuda_device = cuda_device
         self._out = np.empty(self.max_records, dtype=RECORD_DTYPE)
-        self._keepalive = None
+        self._keepalive = []         # host buffers of launches not fetched yet (the H2D copy is asynchronous)
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):
@@ -178,7 +178,7 @@ class Engine:
             arr = arr.reshape(1, -1)
         if arr.shape != (self.n_streams, 2 * self.block_samples) or arr.strides[1] != 1:
             raise ValueError(f"expected uint8 [{self.n_streams}, {2 * self.block_samples}], got {arr.shape}")
-        self._keepalive = arr
+        self._keepalive = (self._keepalive + [arr])[-2:]
         return int(arr.ctypes.data), 0, int(arr.strides[0])
 
     def launch(self, iq) -> None:
@@ -190,7 +190,6 @@ class Engine:
         """Wait for the last launch; candidate records sorted by (stream, fi, start)."""
         n = ctypes.c_int32(0)
         _check(self._lib.rt_engine_fetch(self._h, self._out.ctypes.data_as(ctypes.c_void_p), self.max_records, ctypes.byref(n)))
-        self._keepalive = None
         return self._out[: n.value].copy()
 
     def process(self, iq) -> np.ndarray:
@@ -198,7 +197,6 @@ class Engine:
         n = ctypes.c_int32(0)
         _check(self._lib.rt_engine_process(self._h, ctypes.c_void_p(ptr), on_dev, stride,
                                            self._out.ctypes.data_as(ctypes.c_void_p), self.max_records, ctypes.byref(n)))
-        self._keepalive = None
         return self._out[: n.value].copy()
 
     def reset_stream(self, stream: int) -> None:

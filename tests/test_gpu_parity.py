@@ -173,3 +173,28 @@ def test_engine_rejects_bad_configuration():
                  signal_threshold=1e-9, snr_threshold=3.0, probe_stride=1, min_cols=0, max_cols=10)
     with pytest.raises(IndexError):          # one-column block: analyze.py:354
         BatchAnalyzer(**parity.batch_kwargs(dict(BY_NAME["c1_default_300k"].analyzer_kwargs(), sdr_callback_length=300)))
+
+
+def test_two_blocks_in_flight_equal_sequential_calls():
+    """submit(i+1) before collect(i) (results ring of the engine) == process_blocks one by one."""
+    case = BY_NAME["c1_default_300k"]
+    kw = case.analyzer_kwargs()
+    cap = case.capture()
+    t0 = datetime.datetime(2026, 6, 6, 6, 6, 6)
+    a = BatchAnalyzer(**parity.batch_kwargs(kw))
+    b = BatchAnalyzer(**parity.batch_kwargs(kw))
+    try:
+        want = [a.process_blocks(cap[i][None, :], [t0])[0][0] for i in range(4)]
+        got = []
+        b.submit(cap[0][None, :])
+        for i in range(4):
+            if i + 1 < 4:
+                b.submit(cap[i + 1][None, :])
+            got.append(b.collect([t0])[0][0])
+        assert [[(s.ts, s.frequency, s.max) for s in blk] for blk in got] == [[(s.ts, s.frequency, s.max) for s in blk] for blk in want]
+        assert sum(len(x) for x in got) > 0
+        with pytest.raises(E.EngineError):
+            b.engine.fetch()                 # nothing left in flight
+    finally:
+        a.close()
+        b.close()

@@ -136,3 +136,13 @@ def test_register_fft_dataflow_on_cpu(tmp_path):
         assert np.max(np.abs(got - ref) / ref.max()) < 1e-6
         big = ref > 1e-3 * ref.max()
         assert np.max(np.abs(got[big] - ref[big]) / ref[big]) < 2e-5
+
+
+def test_timedelta_us_matches_cpython_rounding():
+    from pyradiotracking_b200.analyze import timedelta_us
+
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-2, 2, 20000), rng.integers(-2000000, 2000000, 5000) / 1e6 + rng.choice([0, 5e-7, -5e-7], 5000),
+                        np.arange(-3000, 3000) * 0.0000005])
+    want = [(lambda td: (td.days * 86400 + td.seconds) * 1000000 + td.microseconds)(datetime.timedelta(seconds=float(v))) for v in x]
+    assert timedelta_us(x).tolist() == want
