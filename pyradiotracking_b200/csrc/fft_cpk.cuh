@@ -120,24 +120,54 @@ CPK_HD void cdft4_win(cpk& x0, cpk& x1, cpk& x2, cpk& x3, float w0, float w1, fl
     x3 = c_add_j(d02, d13);
 }
 
-// forward 16-point DFT, in place, natural order in and out: 80 packed instructions.
-// n = 4a + b, k = c + 4d:  Y[c+4d] = sum_b W16^{bc} W4^{bd} sum_a x[4a+b] W4^{ac}.
-CPK_HD void cdft16(cpk (&v)[16]) {
-#pragma unroll
-    for (int b = 0; b < 4; ++b) cdft4(v[b], v[4 + b], v[8 + b], v[12 + b]);    // t[b][c] left in v[4c+b]
-    v[4 + 1] = c_mul(v[4 + 1], CPK_C1, -CPK_S1);      // W16^1
-    v[4 + 2] = c_mul(v[4 + 2], CPK_R2, -CPK_R2);      // W16^2
-    v[4 + 3] = c_mul(v[4 + 3], CPK_S1, -CPK_C1);      // W16^3
-    v[8 + 1] = c_mul(v[8 + 1], CPK_R2, -CPK_R2);      // W16^2
-    /* v[8 + 2] * W16^4 = -j: folded into cdft4_x2_mj */
-    v[8 + 3] = c_mul(v[8 + 3], -CPK_R2, -CPK_R2);     // W16^6
-    v[12 + 1] = c_mul(v[12 + 1], CPK_S1, -CPK_C1);    // W16^3
-    v[12 + 2] = c_mul(v[12 + 2], -CPK_R2, -CPK_R2);   // W16^6
-    v[12 + 3] = c_mul(v[12 + 3], -CPK_C1, CPK_S1);    // W16^9
+#define CPK_T1 0.41421356237309504880f   // tan(pi/8)
+
+// Second radix-4 layer of the 16-point DFT: the groups b = 1, 2, 3 take their inputs times W16^{b c}
+// (c = 0..3).  Every W16 power is a real scale (cos(pi/8) or sqrt(1/2)) times a factor of the form
+// (1 -+ j t) or a power of j, so the scale is folded into the butterfly's own additions as FMA operands
+// and each twiddle costs ONE packed instruction instead of two: 11 + 10 + 11 instead of 14 + 12 + 14.
+// b = 1: inputs x (W16^0, W16^1, W16^2, W16^3)
+CPK_HD void cdft4_tw1(cpk& y0, cpk& y1, cpk& y2, cpk& y3) {
+    const cpk a1 = c_fma_swap(y1, CPK_T1, -CPK_T1, y1);        // y1 (1 - j t):   W16^1 y1 =  c1 a1
+    const cpk a3 = c_fma_swap(y3, -CPK_T1, CPK_T1, y3);        // y3 (1 + j t):   W16^3 y3 = -j c1 a3
+    const cpk a2 = c_sub_j(y2, y2);                            // y2 (1 - j):     W16^2 y2 =  r2 a2
+    const cpk p = c_sub_j(a1, a3), q = c_add_j(a1, a3);        // x1 + x3 = c1 p, x1 - x3 = c1 q
+    const cpk s02 = c_fma_s(a2, CPK_R2, y0), d02 = c_fnma_s(a2, CPK_R2, y0);
+    y0 = c_fma_s(p, CPK_C1, s02);
+    y2 = c_fnma_s(p, CPK_C1, s02);
+    y1 = c_fma_swap(q, CPK_C1, -CPK_C1, d02);                  // d02 - j c1 q
+    y3 = c_fma_swap(q, -CPK_C1, CPK_C1, d02);                  // d02 + j c1 q
+}
+// b = 2: inputs x (W16^0, W16^2, W16^4, W16^6)
+CPK_HD void cdft4_tw2(cpk& y0, cpk& y1, cpk& y2, cpk& y3) {
+    const cpk a1 = c_sub_j(y1, y1);                            // W16^2 y1 =  r2 a1
+    const cpk a3 = c_add_j(y3, y3);                            // W16^6 y3 = -r2 a3
+    const cpk p = c_sub(a1, a3), q = c_add(a1, a3);            // x1 + x3 = r2 p, x1 - x3 = r2 q
+    const cpk s02 = c_sub_j(y0, y2), d02 = c_add_j(y0, y2);    // W16^4 = -j
+    y0 = c_fma_s(p, CPK_R2, s02);
+    y2 = c_fnma_s(p, CPK_R2, s02);
+    y1 = c_fma_swap(q, CPK_R2, -CPK_R2, d02);
+    y3 = c_fma_swap(q, -CPK_R2, CPK_R2, d02);
+}
+// b = 3: inputs x (W16^0, W16^3, W16^6, W16^9)
+CPK_HD void cdft4_tw3(cpk& y0, cpk& y1, cpk& y2, cpk& y3) {
+    const cpk a1 = c_fma_swap(y1, -CPK_T1, CPK_T1, y1);        // y1 (1 + j t):   W16^3 y1 = -j c1 a1
+    const cpk a3 = c_fma_swap(y3, CPK_T1, -CPK_T1, y3);        // y3 (1 - j t):   W16^9 y3 = -c1 a3
+    const cpk a2 = c_add_j(y2, y2);                            // y2 (1 + j):     W16^6 y2 = -r2 a2
+    const cpk p = c_add_j(a3, a1), q = c_sub_j(a3, a1);        // x1 + x3 = -c1 p, x1 - x3 = c1 q
+    const cpk s02 = c_fnma_s(a2, CPK_R2, y0), d02 = c_fma_s(a2, CPK_R2, y0);
+    y0 = c_fnma_s(p, CPK_C1, s02);
+    y2 = c_fma_s(p, CPK_C1, s02);
+    y1 = c_fma_swap(q, CPK_C1, -CPK_C1, d02);
+    y3 = c_fma_swap(q, -CPK_C1, CPK_C1, d02);
+}
+
+// second layer + output index transpose shared by cdft16 / cdft16_win
+CPK_HD void cdft16_tail(cpk (&v)[16]) {
     cdft4(v[0], v[1], v[2], v[3]);
-    cdft4(v[4], v[5], v[6], v[7]);
-    cdft4_x2_mj(v[8], v[9], v[10], v[11]);
-    cdft4(v[12], v[13], v[14], v[15]);
+    cdft4_tw1(v[4], v[5], v[6], v[7]);
+    cdft4_tw2(v[8], v[9], v[10], v[11]);
+    cdft4_tw3(v[12], v[13], v[14], v[15]);
     // v[4c+d] holds Y[c+4d]: transpose the 4x4 index grid (register renaming only)
 #pragma unroll
     for (int c = 0; c < 4; ++c)
@@ -149,32 +179,19 @@ CPK_HD void cdft16(cpk (&v)[16]) {
         }
 }
 
-// same, on un-windowed inputs: v[i] <- DFT16(w[i] * v[i])   (72 packed instructions + 0 for the window)
+// forward 16-point DFT, in place, natural order in and out: 72 packed instructions.
+// n = 4a + b, k = c + 4d:  Y[c+4d] = sum_b W16^{bc} W4^{bd} sum_a x[4a+b] W4^{ac}.
+CPK_HD void cdft16(cpk (&v)[16]) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) cdft4(v[b], v[4 + b], v[8 + b], v[12 + b]);    // t[b][c] left in v[4c+b]
+    cdft16_tail(v);
+}
+
+// same, on un-windowed inputs: v[i] <- DFT16(w[i] * v[i])   (80 packed instructions including the window)
 CPK_HD void cdft16_win(cpk (&v)[16], const float (&w)[16]) {
 #pragma unroll
-    for (int b = 0; b < 4; ++b) cdft4_win(v[b], v[4 + b], v[8 + b], v[12 + b], w[b], w[4 + b], w[8 + b], w[12 + b]);    // t[b][c] left in v[4c+b]
-    v[4 + 1] = c_mul(v[4 + 1], CPK_C1, -CPK_S1);      // W16^1
-    v[4 + 2] = c_mul(v[4 + 2], CPK_R2, -CPK_R2);      // W16^2
-    v[4 + 3] = c_mul(v[4 + 3], CPK_S1, -CPK_C1);      // W16^3
-    v[8 + 1] = c_mul(v[8 + 1], CPK_R2, -CPK_R2);      // W16^2
-    /* v[8 + 2] * W16^4 = -j: folded into cdft4_x2_mj */
-    v[8 + 3] = c_mul(v[8 + 3], -CPK_R2, -CPK_R2);     // W16^6
-    v[12 + 1] = c_mul(v[12 + 1], CPK_S1, -CPK_C1);    // W16^3
-    v[12 + 2] = c_mul(v[12 + 2], -CPK_R2, -CPK_R2);   // W16^6
-    v[12 + 3] = c_mul(v[12 + 3], -CPK_C1, CPK_S1);    // W16^9
-    cdft4(v[0], v[1], v[2], v[3]);
-    cdft4(v[4], v[5], v[6], v[7]);
-    cdft4_x2_mj(v[8], v[9], v[10], v[11]);
-    cdft4(v[12], v[13], v[14], v[15]);
-    // v[4c+d] holds Y[c+4d]: transpose the 4x4 index grid (register renaming only)
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int d = c + 1; d < 4; ++d) {
-            const cpk t = v[4 * c + d];
-            v[4 * c + d] = v[4 * d + c];
-            v[4 * d + c] = t;
-        }
+    for (int b = 0; b < 4; ++b) cdft4_win(v[b], v[4 + b], v[8 + b], v[12 + b], w[b], w[4 + b], w[8 + b], w[12 + b]);
+    cdft16_tail(v);
 }
 
 }  // namespace rt

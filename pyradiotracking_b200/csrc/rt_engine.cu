@@ -25,7 +25,7 @@
 #include <vector>
 
 #include "../../include/rt_engine.h"
-#include "fft_cpk.cuh"
+#include "spectro256.cuh"
 
 namespace {
 
@@ -65,15 +65,7 @@ __device__ __forceinline__ int bin_pos(int fi) {
 // ---------------------------------------------------------------------------------------------
 // spectrogram, generic: any power-of-two nperseg in [8, 4096]; Stockham radix-4 in shared memory
 // ---------------------------------------------------------------------------------------------
-struct SpectroArgs {
-    const uint8_t* iq;
-    size_t stream_stride;
-    int n, T, chunk_segs, n_chunks;
-    const float* win;      // window * sqrt(1/(fs*sum(w^2))) / 127.5
-    const float2* tw;      // exp(-2 pi i k / n)
-    float* S;              // [stream][T][n]
-    float* part;           // [stream][chunk][n]   (FFT bin order)
-};
+using rt::SpectroArgs;
 
 template <int NT>
 __global__ void __launch_bounds__(NT) spectro_generic(SpectroArgs a) {
@@ -169,208 +161,6 @@ __global__ void __launch_bounds__(NT) spectro_generic(SpectroArgs a) {
     }
     float* pd = a.part + ((size_t)s * a.n_chunks + blockIdx.x) * n;
     for (int i = tid; i < n; i += NT) pd[i] = rowacc[i];
-}
-
-// ---------------------------------------------------------------------------------------------
-// spectrogram, nperseg == 256: 16 threads per segment, 16x16 Cooley-Tukey held in registers,
-// one shared-memory transpose between the two radix-16 passes
-// ---------------------------------------------------------------------------------------------
-constexpr int R256_WARPS = 4;              // warps per CTA
-constexpr int R256_THREADS = R256_WARPS * 32;
-constexpr int R256_SEGS_PER_ROUND = 2 * R256_WARPS;   // a warp does 2 segments per round, one per half-warp
-constexpr int R256_STAGES = 4;             // TMA ring depth per warp (rounds in flight)
-constexpr int R256_RAW_STRIDE = 544;       // 512 B of IQ + 32 B pad: the two segments of a warp hit disjoint banks
-constexpr int R256_XROW = 36;              // floats per exchange row: 16 complex + 16 B pad (conflict-free LDS.128)
-constexpr int R256_XTILE = 16 * R256_XROW; // a half-warp's exchange tile
-constexpr int R256_CHUNK = 256;            // segments per CTA
-constexpr int R256_RAW_BYTES = R256_WARPS * R256_STAGES * 2 * R256_RAW_STRIDE;
-constexpr int R256_XCH_BYTES = 2 * R256_WARPS * R256_XTILE * 4;
-constexpr int R256_BAR_OFF = R256_RAW_BYTES + R256_XCH_BYTES;
-constexpr int R256_SMEM = R256_BAR_OFF + R256_WARPS * R256_STAGES * 8;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-// exact byte sums of I and Q over one 256-sample segment held in shared memory (bytes I0 Q0 I1 Q1 ...);
-// lane j of the half-warp adds 32 of the 512 bytes, the half-warp total comes back packed I | Q << 16
-__device__ __forceinline__ unsigned seg_byte_sums(const unsigned char* rb, int j) {
-    const uint4 q0 = *reinterpret_cast<const uint4*>(rb + 16 * j);
-    const uint4 q1 = *reinterpret_cast<const uint4*>(rb + 256 + 16 * j);
-    unsigned sI = 0, sQ = 0;
-    sI = __dp4a(q0.x, 0x00010001u, sI); sQ = __dp4a(q0.x, 0x01000100u, sQ);
-    sI = __dp4a(q0.y, 0x00010001u, sI); sQ = __dp4a(q0.y, 0x01000100u, sQ);
-    sI = __dp4a(q0.z, 0x00010001u, sI); sQ = __dp4a(q0.z, 0x01000100u, sQ);
-    sI = __dp4a(q0.w, 0x00010001u, sI); sQ = __dp4a(q0.w, 0x01000100u, sQ);
-    sI = __dp4a(q1.x, 0x00010001u, sI); sQ = __dp4a(q1.x, 0x01000100u, sQ);
-    sI = __dp4a(q1.y, 0x00010001u, sI); sQ = __dp4a(q1.y, 0x01000100u, sQ);
-    sI = __dp4a(q1.z, 0x00010001u, sI); sQ = __dp4a(q1.z, 0x01000100u, sQ);
-    sI = __dp4a(q1.w, 0x00010001u, sI); sQ = __dp4a(q1.w, 0x01000100u, sQ);
-    unsigned tot = sI | (sQ << 16);                // each total <= 255*256 < 2^16
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);   // stays inside the half-warp
-    return tot;
-}
-
-__device__ __forceinline__ rt::cpk detrend_const(unsigned tot) {
-    // (32768 + mean_I, 32768 + mean_Q): exact in fp32 (the mean of 256 bytes is a multiple of 2^-8 = ulp(2^15))
-    return rt::c_make(32768.f + (float)(tot & 0xffffu) * 0.00390625f, 32768.f + (float)(tot >> 16) * 0.00390625f);
-}
-
-__global__ void __launch_bounds__(R256_THREADS, 4) spectro_reg256(SpectroArgs a) {
-    // 16 threads (a half-warp) hold one 256-point FFT as a 16x16 Cooley-Tukey in registers; every complex
-    // value is one packed register pair (fft_cpk.cuh).  A warp works on two consecutive segments per round.
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    unsigned char* raw = dyn_smem;                                                   // [warp][stage][half][544]
-    float* xch = reinterpret_cast<float*>(dyn_smem + R256_RAW_BYTES);                // [half-warp][16][R256_XROW]
-    uint64_t* full = reinterpret_cast<uint64_t*>(dyn_smem + R256_BAR_OFF);           // [warp][stage]
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31, h = lane >> 4, j = lane & 15;
-    const int hw = tid >> 4;
-    const int s = blockIdx.y;
-    const int seg0 = blockIdx.x * a.chunk_segs;
-    const int seg1 = min(a.T, seg0 + a.chunk_segs);
-    const uint8_t* base = a.iq + (size_t)s * a.stream_stride;
-    // round `it` of this warp covers segments first + 8*it + {0, 1}
-    const int first = seg0 + 2 * warp;
-    const int n_it = (seg1 - first + R256_SEGS_PER_ROUND - 1) / R256_SEGS_PER_ROUND;
-    unsigned char* wraw = raw + warp * (R256_STAGES * 2 * R256_RAW_STRIDE);
-    uint64_t* wfull = full + warp * R256_STAGES;
-    float* xt = xch + hw * R256_XTILE;              // [k1][n2] complex
-
-    if (lane == 0) {
-#pragma unroll
-        for (int st = 0; st < R256_STAGES; ++st) mbar_init(&wfull[st], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#pragma unroll
-        for (int st = 0; st < R256_STAGES; ++st)
-            if (st < n_it) {
-                const int sg = first + R256_SEGS_PER_ROUND * st;
-                const int nv = min(2, seg1 - sg);
-                mbar_expect_tx(&wfull[st], 512 * nv);
-                bulk_g2s(wraw + (st * 2) * R256_RAW_STRIDE, base + (size_t)sg * 512, 512, &wfull[st]);
-                if (nv == 2) bulk_g2s(wraw + (st * 2 + 1) * R256_RAW_STRIDE, base + (size_t)(sg + 1) * 512, 512, &wfull[st]);
-            }
-    }
-
-    // per-thread constants: window at samples 16*n1 + j, inter-pass twiddles W256^{j*k1} as (wr, (-wi, wi))
-    float wj[16], twr[16], acc[16];
-    unsigned long long twp[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        wj[i] = a.win[16 * i + j];
-        const float2 t = a.tw[(j * i) & 255];
-        twr[i] = t.x;
-        twp[i] = rt::cpk_pair(-t.y, t.y);
-        acc[i] = 0.f;
-    }
-    __syncwarp();                                   // barriers initialised before anyone polls them
-
-    // detrend constants of the first round (later rounds: computed one round ahead, off the critical path)
-    rt::cpk cm = rt::c_make(0.f, 0.f);
-    if (n_it > 0) {
-        while (!mbar_try_wait(&wfull[0], 0)) {}
-        cm = detrend_const(seg_byte_sums(wraw + h * R256_RAW_STRIDE, j));
-    }
-
-    for (int it = 0; it < n_it; ++it) {
-        const int seg = first + R256_SEGS_PER_ROUND * it + h;
-        const bool valid = seg < seg1;              // odd tail: the upper half-warp idles through the last round
-        const int st = it % R256_STAGES;
-        const unsigned char* rb = wraw + (st * 2 + h) * R256_RAW_STRIDE;
-
-        // uint8 -> float (0x4700bb00 is 32768 + b, no I2F), detrend (scipy detrend='constant'), window
-        rt::cpk v[16];
-#pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) {
-            const unsigned u = *reinterpret_cast<const unsigned short*>(rb + 32 * n1 + 2 * j);
-            const rt::cpk f = rt::c_make(__uint_as_float(__byte_perm(u, 0x47000000u, 0x7604)),
-                                         __uint_as_float(__byte_perm(u, 0x47000000u, 0x7614)));
-            v[n1] = rt::c_scale(rt::c_sub(f, cm), wj[n1]);
-        }
-        // this stage's bytes are in registers: refill it with the segments R256_STAGES rounds ahead
-        __syncwarp();
-        if (lane == 0 && it + R256_STAGES < n_it) {
-            const int sg = first + R256_SEGS_PER_ROUND * (it + R256_STAGES);
-            const int nv = min(2, seg1 - sg);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&wfull[st], 512 * nv);
-            bulk_g2s(wraw + (st * 2) * R256_RAW_STRIDE, base + (size_t)sg * 512, 512, &wfull[st]);
-            if (nv == 2) bulk_g2s(wraw + (st * 2 + 1) * R256_RAW_STRIDE, base + (size_t)(sg + 1) * 512, 512, &wfull[st]);
-        }
-        // byte sums of the NEXT round: the shuffle chain overlaps the butterflies below
-        unsigned tot = 0;
-        if (it + 1 < n_it) {
-            const int sn = (it + 1) % R256_STAGES;
-            while (!mbar_try_wait(&wfull[sn], ((it + 1) / R256_STAGES) & 1)) {}
-            tot = seg_byte_sums(wraw + (sn * 2 + h) * R256_RAW_STRIDE, j);
-        }
-
-        rt::cdft16(v);                              // over n1 -> k1, for column n2 = j
-        // inter-pass twiddles, then the 16x16 transpose through shared memory
-        *reinterpret_cast<unsigned long long*>(&xt[2 * j]) = v[0].v;
-#pragma unroll
-        for (int k1 = 1; k1 < 16; ++k1) {
-            const rt::cpk t = rt::c_fma_swap_p(v[k1], twp[k1], rt::c_scale(v[k1], twr[k1]));
-            *reinterpret_cast<unsigned long long*>(&xt[k1 * R256_XROW + 2 * j]) = t.v;
-        }
-        cm = detrend_const(tot);
-        __syncwarp();
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(&xt[j * R256_XROW + 4 * c]);
-            v[2 * c].v = q.x;
-            v[2 * c + 1].v = q.y;
-        }
-        // (the tile is rewritten only after the next round's __syncwarp)
-        rt::cdft16(v);                              // over n2 -> k2, for k1 = j: bin = j + 16*k2
-        if (valid) {
-            float p[16];
-#pragma unroll
-            for (int k2 = 0; k2 < 16; ++k2) {
-                const float re = rt::c_re(v[k2]), im = rt::c_im(v[k2]);
-                p[k2] = re * re + im * im;
-                acc[k2] += p[k2];
-            }
-            float4* dst = reinterpret_cast<float4*>(a.S + ((size_t)s * a.T + seg) * 256 + 4 * j);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) dst[16 * c] = make_float4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
-        }
-    }
-
-    // chunk row sums: fixed-order reduction over the half-warps, written in FFT bin order (fi = j + 16*k2)
-    __syncthreads();
-    float* red = xch;
-#pragma unroll
-    for (int k2 = 0; k2 < 16; ++k2) red[hw * 256 + 16 * k2 + j] = acc[k2];
-    __syncthreads();
-    float* pd = a.part + ((size_t)s * a.n_chunks + blockIdx.x) * 256;
-    for (int fi = tid; fi < 256; fi += R256_THREADS) {
-        float t = 0.f;
-#pragma unroll
-        for (int hh = 0; hh < 2 * R256_WARPS; ++hh) t += red[hh * 256 + fi];
-        pd[fi] = t;
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -721,7 +511,7 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     e->n_probes = (e->T + cfg->probe_stride - 1) / cfg->probe_stride;
     if (cfg->fft_impl == RT_FFT_REG256 && n != 256) { delete e; return fail(RT_ERR_INVALID, "RT_FFT_REG256 needs nperseg == 256"); }
     e->reg256 = (n == 256) && (cfg->fft_impl != RT_FFT_GENERIC);
-    e->chunk_segs = e->reg256 ? R256_CHUNK : 32;
+    e->chunk_segs = e->reg256 ? 256 : 32;
     e->n_chunks = (e->T + e->chunk_segs - 1) / e->chunk_segs;
 
 #define CUE(call)                                                                                  \
@@ -780,8 +570,8 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
         const size_t smem = (size_t)n * (2 * sizeof(float2) + sizeof(float)) + 16;
         CUE(cudaFuncSetAttribute(spectro_generic<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     } else {
-        CUE(cudaFuncSetAttribute(spectro_reg256, cudaFuncAttributeMaxDynamicSharedMemorySize, R256_SMEM));
-        CUE(cudaFuncSetAttribute(spectro_reg256, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
+        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     }
 #undef CUE
     *out = e;
@@ -869,7 +659,7 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     if (e->reg256 && !aligned) return fail(RT_ERR_INVALID, "register FFT path needs 16-byte aligned IQ and stream stride");
     dim3 grid(e->n_chunks, e->n_streams);
     if (use_reg) {
-        spectro_reg256<<<grid, R256_THREADS, R256_SMEM, st>>>(sa);
+        rt::spectro_reg256_v7<true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
     } else {
         const size_t smem = (size_t)e->n * (2 * sizeof(float2) + sizeof(float)) + 16;
         spectro_generic<256><<<grid, 256, smem, st>>>(sa);

@@ -334,7 +334,8 @@ struct R256v7 {
     static constexpr int XCH_BYTES = 2 * WARPS * XTILE * 4;
     static constexpr int RED_BYTES = 2 * WARPS * 256 * 4;
     static constexpr int BAR_OFF = (RAW_BYTES + XCH_BYTES) > RED_BYTES ? (RAW_BYTES + XCH_BYTES) : RED_BYTES;
-    static constexpr int SMEM = BAR_OFF + WARPS * STAGES * 8;
+    static constexpr int TAB_OFF = BAR_OFF + WARPS * STAGES * 8;         // optional constant tables: tw[16][16] float2, win[256]
+    static constexpr int SMEM = TAB_OFF + 2048 + 1024;
     static constexpr int SEGS_PER_ROUND = 2 * WARPS;
 };
 
@@ -357,6 +358,10 @@ __device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void* src, unsign
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void bulk_g2s_hint_a(uint32_t dst, const void* src, unsigned bytes, uint32_t bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
 __device__ __forceinline__ unsigned lds_u16(uint32_t addr) {
     unsigned short v;
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
@@ -369,6 +374,14 @@ __device__ __forceinline__ uint4 lds_128(uint32_t addr) {
 }
 __device__ __forceinline__ void lds_2x64(uint32_t addr, unsigned long long& a, unsigned long long& b) {
     asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void lds_2f32(uint32_t addr, float& a, float& b) {
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(addr));
 }
 __device__ __forceinline__ void sts_64(uint32_t addr, unsigned long long v) {
     asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
@@ -387,8 +400,8 @@ __device__ __forceinline__ void lane_byte_sums(uint32_t addr, unsigned& sI, unsi
     sI = __dp4a(q1.w, 0x00010001u, sI); sQ = __dp4a(q1.w, 0x01000100u, sQ);
 }
 
-template <bool STORE>
-__global__ void __launch_bounds__(R256v7::THREADS, R256v7::MINB) spectro_reg256_v7(SpectroArgs a) {
+template <bool STORE, bool HINT = false, int MINB = 4, bool TWS = false, bool WINS = false>
+__global__ void __launch_bounds__(R256v7::THREADS, MINB) spectro_reg256_v7(SpectroArgs a) {
     using C = R256v7;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     const int tid = threadIdx.x;
@@ -412,14 +425,21 @@ __global__ void __launch_bounds__(R256v7::THREADS, R256v7::MINB) spectro_reg256_
     const uint8_t* gsrc = a.iq + (size_t)s * a.stream_stride + (size_t)first * 512;
     const int last_seg = seg1 - 1;
 
+    uint64_t pol_in = 0, pol_out = 0;
+    if (HINT) { pol_in = policy_evict_first(); pol_out = policy_evict_last(); }
     auto issue = [&](int itx, int st) {                              // executed by one elected lane
         const int sg = first + C::SEGS_PER_ROUND * itx;
         const uint8_t* p0 = gsrc + (size_t)itx * (C::SEGS_PER_ROUND * 512);
         const uint8_t* p1 = (sg + 1 <= last_seg) ? p0 + 512 : p0;   // ragged tail: copy the same segment twice
         const uint32_t bar = wbar + 8 * st, dst = wraw + st * C::STAGE_BYTES;
         mbar_expect_tx_a(bar, 1024);
-        bulk_g2s_a(dst, p0, 512, bar);
-        bulk_g2s_a(dst + C::RAW_STRIDE, p1, 512, bar);
+        if (HINT) {
+            bulk_g2s_hint_a(dst, p0, 512, bar, pol_in);
+            bulk_g2s_hint_a(dst + C::RAW_STRIDE, p1, 512, bar, pol_in);
+        } else {
+            bulk_g2s_a(dst, p0, 512, bar);
+            bulk_g2s_a(dst + C::RAW_STRIDE, p1, 512, bar);
+        }
     };
 
     if (elect_one()) {
@@ -433,7 +453,18 @@ __global__ void __launch_bounds__(R256v7::THREADS, R256v7::MINB) spectro_reg256_
     }
 
     // per-thread constants: window at samples 16*n1 + j, inter-pass twiddles W256^{j*k1}
+    // (in registers, or -- TWS / WINS -- in a shared-memory table to buy a fifth / sixth resident CTA)
     float wj[16], twr[16], twi[16], acc[16];
+    const uint32_t tab_tw = sm0 + C::TAB_OFF + 8 * j, tab_win = sm0 + C::TAB_OFF + 2048 + 4 * j;
+    if (TWS || WINS) {
+        float2* ttw = reinterpret_cast<float2*>(dyn_smem + C::TAB_OFF);
+        float* twin = reinterpret_cast<float*>(dyn_smem + C::TAB_OFF + 2048);
+        for (int i = tid; i < 256; i += C::THREADS) {
+            ttw[i] = a.tw[((i & 15) * (i >> 4)) & 255];      // [k1][j]
+            twin[i] = a.win[i];                              // [n1][j]
+        }
+        __syncthreads();
+    }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         wj[i] = a.win[16 * i + j];
@@ -489,11 +520,19 @@ __global__ void __launch_bounds__(R256v7::THREADS, R256v7::MINB) spectro_reg256_
             cm_next = detrend_of(my_sum + st_off);
         }
 
+        if (WINS) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) wj[i] = lds_f32(tab_win + 64 * i);
+        }
         cdft16_win(v, wj);                          // over n1 -> k1, for column n2 = j
         // inter-pass twiddles, then the 16x16 transpose through shared memory
         sts_64(xt_st, v[0].v);
 #pragma unroll
-        for (int k1 = 1; k1 < 16; ++k1) sts_64(xt_st + k1 * (C::XROW * 4), c_mul(v[k1], twr[k1], twi[k1]).v);
+        for (int k1 = 1; k1 < 16; ++k1) {
+            float wr = twr[k1], wi = twi[k1];
+            if (TWS) lds_2f32(tab_tw + 128 * k1, wr, wi);
+            sts_64(xt_st + k1 * (C::XROW * 4), c_mul(v[k1], wr, wi).v);
+        }
         __syncwarp();
 #pragma unroll
         for (int c = 0; c < 8; ++c) lds_2x64(xt_ld + 16 * c, v[2 * c].v, v[2 * c + 1].v);
@@ -512,7 +551,11 @@ __global__ void __launch_bounds__(R256v7::THREADS, R256v7::MINB) spectro_reg256_
             if (valid) {
                 float4* dst = reinterpret_cast<float4*>(sdst);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) dst[16 * c] = make_float4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
+                for (int c = 0; c < 4; ++c) {
+                    const float4 o = make_float4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
+                    if (HINT) stg128_hint(dst + 16 * c, o, pol_out);
+                    else dst[16 * c] = o;
+                }
             }
             sdst += C::SEGS_PER_ROUND * 256;
         }

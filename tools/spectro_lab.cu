@@ -16,6 +16,8 @@ using namespace rt;
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
 static const char* g_filter = nullptr;
+static cudaStream_t g_st[4];
+static int g_nst = 1;
 
 struct Ctx {
     int streams, T, reps;
@@ -42,14 +44,22 @@ void run_k(Ctx& c, kern_t kern, int THREADS, int SMEM, const char* name, int chu
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     auto launch = [&]() {
         if (group <= 0) {
-            kern<<<dim3(a.n_chunks, c.streams), THREADS, SMEM>>>(a);
+            kern<<<dim3(a.n_chunks, c.streams), THREADS, SMEM, g_st[0]>>>(a);
         } else {
+            if (g_nst > 1) {   // fork
+                cudaEvent_t ev; cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); cudaEventRecord(ev, g_st[0]);
+                for (int q = 1; q < g_nst; ++q) cudaStreamWaitEvent(g_st[q], ev, 0);
+                cudaEventDestroy(ev);
+            }
             for (int g = 0, k = 0; g < c.streams; g += group, ++k) {
                 SpectroArgs b = a;
                 b.iq = c.d_iq + (size_t)g * c.stride;
-                b.S = c.d_S + (size_t)(k & 1) * group * c.T * 256;      // ping-pong group buffers
+                b.S = c.d_S + (size_t)(k % std::max(2, g_nst)) * group * c.T * 256;      // ring of group buffers
                 b.part = c.d_part + (size_t)g * a.n_chunks * 256;
-                kern<<<dim3(a.n_chunks, std::min(group, c.streams - g)), THREADS, SMEM>>>(b);
+                kern<<<dim3(a.n_chunks, std::min(group, c.streams - g)), THREADS, SMEM, g_st[k % g_nst]>>>(b);
+            }
+            if (g_nst > 1) {   // join the side streams back into stream 0 (the timing events live there)
+                for (int q = 1; q < g_nst; ++q) { cudaEvent_t ev; cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); cudaEventRecord(ev, g_st[q]); cudaStreamWaitEvent(g_st[0], ev, 0); cudaEventDestroy(ev); }
             }
         }
     };
@@ -57,9 +67,9 @@ void run_k(Ctx& c, kern_t kern, int THREADS, int SMEM, const char* name, int chu
     CK(cudaDeviceSynchronize());
     float best = 1e9f, tot = 0;
     for (int i = 0; i < c.reps; ++i) {
-        CK(cudaEventRecord(e0));
+        CK(cudaEventRecord(e0, g_st[0]));
         launch();
-        CK(cudaEventRecord(e1));
+        CK(cudaEventRecord(e1, g_st[0]));
         CK(cudaEventSynchronize(e1));
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
         best = std::min(best, ms); tot += ms;
@@ -95,6 +105,7 @@ template <class C>
 void run(Ctx& c, const char* name, int chunk, int group = 0) { run_k(c, spectro_reg256_k<C>, C::THREADS, C::SMEM, name, chunk, group); }
 
 int main(int argc, char** argv) {
+    for (auto& st : g_st) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     Ctx c;
     c.streams = argc > 1 ? atoi(argv[1]) : 64;
     c.reps = argc > 2 ? atoi(argv[2]) : 10;
@@ -149,6 +160,23 @@ int main(int argc, char** argv) {
     run_k(c, spectro_reg256_v7<true>, R256v7::THREADS, R256v7::SMEM, "v7", 256);
     run_k(c, spectro_reg256_v7<false>, R256v7::THREADS, R256v7::SMEM, "v7 no store", 256);
     run_k(c, spectro_reg256_v7<true>, R256v7::THREADS, R256v7::SMEM, "v7 chunk 128", 128);
+    run_k(c, spectro_reg256_v7<true, false, 5, true, false>, R256v7::THREADS, R256v7::SMEM, "v7 tw-smem minb5", 256);
+    run_k(c, spectro_reg256_v7<true, false, 6, true, false>, R256v7::THREADS, R256v7::SMEM, "v7 tw-smem minb6", 256);
+    run_k(c, spectro_reg256_v7<true, false, 5, false, true>, R256v7::THREADS, R256v7::SMEM, "v7 win-smem minb5", 256);
+    run_k(c, spectro_reg256_v7<true, false, 6, true, true>, R256v7::THREADS, R256v7::SMEM, "v7 tw+win-smem minb6", 256);
+    run_k(c, spectro_reg256_v7<true, false, 5, true, true>, R256v7::THREADS, R256v7::SMEM, "v7 tw+win-smem minb5", 256);
+    run_k(c, spectro_reg256_v7<false, false, 6, true, false>, R256v7::THREADS, R256v7::SMEM, "v7 tw-smem minb6 no store", 256);
+    run_k(c, spectro_reg256_v7<true, true>, R256v7::THREADS, R256v7::SMEM, "v7 hints", 256);
+    run_k(c, spectro_reg256_v7<true>, R256v7::THREADS, R256v7::SMEM, "v7 grp4 1 stream", 64, 4);
+    run_k(c, spectro_reg256_v7<true, true>, R256v7::THREADS, R256v7::SMEM, "v7 grp4 1 stream hints", 64, 4);
+    g_nst = 2;
+    run_k(c, spectro_reg256_v7<true>, R256v7::THREADS, R256v7::SMEM, "v7 grp4 2 streams", 64, 4);
+    run_k(c, spectro_reg256_v7<true, true>, R256v7::THREADS, R256v7::SMEM, "v7 grp4 2 streams hints", 64, 4);
+    run_k(c, spectro_reg256_v7<true, true>, R256v7::THREADS, R256v7::SMEM, "v7 grp2 2 streams hints", 32, 2);
+    run_k(c, spectro_reg256_v7<true, true>, R256v7::THREADS, R256v7::SMEM, "v7 grp8 2 streams hints", 128, 8);
+    g_nst = 4;
+    run_k(c, spectro_reg256_v7<true, true>, R256v7::THREADS, R256v7::SMEM, "v7 grp4 4 streams hints", 64, 4);
+    g_nst = 1;
     run<Wf>(c, "wfold", 256);
     run<Wfn>(c, "wfold no store", 256);
     run<Pa>(c, "wfold+packacc", 256);
