@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--streams", type=int, default=64, help="streams per GPU")
     ap.add_argument("--cpu-sample", type=int, default=8, help="stream-blocks timed for cpu_baseline")
     ap.add_argument("--profile", action="store_true", help="device-resident region only (for runs under ncu)")
+    ap.add_argument("--fft-impl", default="auto", choices=["auto", "reg256", "tc256", "generic"],
+                    help="spectrogram kernel: auto = reg256 (registers, packed fp32x2); tc256 = tensor-core stage 1 (tcgen05)")
     return ap.parse_args()
 
 
@@ -238,7 +240,9 @@ def run_b200(args):
     for s in range(S):
         hnp[:, s, :] = distinct[s % len(distinct)]
     dev = host.cuda()
-    ba = BatchAnalyzer(**analyzer_kwargs(w, S, rank), cuda_device=local)
+    from pyradiotracking_b200 import engine as _E
+    impl = {"auto": _E.FFT_AUTO, "reg256": _E.FFT_REG256, "tc256": _E.FFT_TC256, "generic": _E.FFT_GENERIC}[args.fft_impl]
+    ba = BatchAnalyzer(**analyzer_kwargs(w, S, rank), cuda_device=local, fft_impl=impl)
     eng = ba.engine
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
@@ -257,6 +261,7 @@ def run_b200(args):
     ev0.record(stream)
     for i in range(args.steps):
         eng.launch(dev[(args.warmup + i) % n_blk])
+    eng.join()          # the scan kernels of the last launch run on the engine's scan stream: wait for them too
     ev1.record(stream)
     barrier()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
@@ -302,14 +307,15 @@ def run_b200(args):
             "config": {"workload": "configs[1]: 64x2.4MS/s nperseg256 hamming -90dBW/5dB 8-40ms", "streams_per_gpu": S,
                        "block_samples": w.block_samples, "distinct_streams": min(N_DISTINCT, S),
                        "l2": "inputs larger than L2 (307 MB per step, 2 alternating blocks)",
-                       "records_per_step": n_rec},
+                       "records_per_step": n_rec, "fft_impl": args.fft_impl,
+                       "scan_overlap": os.environ.get("RT_SCAN_OVERLAP", "1") != "0"},
             "clocks": clk,
             "e2e": None if args.profile else {
                 "value": world * samples_per_step * e2e_steps / e2e_s / 1e6, "unit": UNIT,
                 "h2d_bytes_per_step": S * w.block_bytes, "d2h_bytes_per_step": d2h // e2e_steps,
                 "signals_per_step": n_sig / e2e_steps},
             "gpu_launches": int(tim["kernels"]),
-            "roofline": {"bound": "hbm", "kernel": "spectro_reg256", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "spectro_tc256" if args.fft_impl == "tc256" else "spectro_reg256", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": recorded_traffic(), "peak_source": peak_kind,
                          "algorithmic_bytes_per_launch": 2 * samples_per_step, "kernel_ms": k_ms,
                          "kernel_share_of_step": k_ms / (ms / args.steps),

@@ -36,7 +36,12 @@ enum {
 };
 
 /* fft_impl selector: which spectrogram kernel runs (tests compare them). */
-enum { RT_FFT_AUTO = 0, RT_FFT_GENERIC = 1, RT_FFT_REG256 = 2 };
+enum {
+    RT_FFT_AUTO = 0,      /* nperseg 256: RT_FFT_REG256, otherwise RT_FFT_GENERIC */
+    RT_FFT_GENERIC = 1,   /* shared-memory Stockham FFT, any power-of-two nperseg */
+    RT_FFT_REG256 = 2,    /* nperseg 256: 16x16 FFT in registers (packed fp32x2), TMA-fed */
+    RT_FFT_TC256 = 3      /* nperseg 256, boxcar/hann/hamming: first FFT stage on the tensor cores (tcgen05, fp16 x split-fp16 -> fp32) */
+};
 
 /*
  * Engine configuration = the analysis keys of SignalAnalyzer.__init__
@@ -123,6 +128,14 @@ int rt_engine_launch(rt_engine *e, const uint8_t *iq, int32_t iq_on_device, size
 /* ... then wait for the OLDEST unfetched launch, copy back and sort its records.  Two launches may be in
  * flight (launch i+1 can be queued before fetch i); a third launch drops the oldest unfetched result. */
 int rt_engine_fetch(rt_engine *e, rt_record *out, int32_t max_out, int32_t *n_out);
+
+/*
+ * The scan kernels (row mean, probe, extraction) of a launch run on an engine-internal stream so that they
+ * overlap the spectrogram of the NEXT launch.  rt_engine_join makes the launch stream (the engine's own or the
+ * one given to rt_engine_set_stream) wait for everything launched so far, e.g. before the caller records an
+ * event on it or reuses a device-resident `iq` buffer from another stream.  rt_engine_fetch does not need it.
+ */
+int rt_engine_join(rt_engine *e);
 
 /* Spectrogram geometry: *T = block_samples / nperseg columns per block. */
 int rt_engine_shape(const rt_engine *e, int32_t *n_streams, int32_t *nperseg, int32_t *T);

@@ -6,8 +6,9 @@
 // extract_signals' probe / backward / forward scans and per-signal statistics.
 //
 // Kernels (one launch each per engine call, all streams of the batch at once):
-//   spectro_*      uint8 IQ -> power cells S[stream][t][bin] (fp32) + per-chunk row sums
-//   row_mean       deterministic reduction of the chunk sums -> freq_avg[stream][bin]
+//   spectro_*      uint8 IQ -> power cells S (fp32, layout per kernel) + row sums / row means
+//   row_mean       deterministic reduction of the chunk sums -> freq_avg[stream][bin] (the tensor-core
+//                  kernel does this itself in the last warp-group run of each stream)
 //   probe          one thread per (stream, bin, probe column k*stride): predicate test,
 //                  cheap pruning of short noise runs, survivors -> work list
 //   extract        one warp per work item: run limits by ballot, carry into the
@@ -20,17 +21,20 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../include/rt_engine.h"
 #include "spectro256.cuh"
+#include "spectro_tc256.cuh"
 
 namespace {
 
 thread_local std::string g_err;
 constexpr int RT_SLOTS = 2;     // launches that may be in flight before rt_engine_fetch
+constexpr int RT_SBUFS = 3;     // spectrogram buffers (block being written, block being scanned, its carry)
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -53,14 +57,30 @@ __device__ __forceinline__ bool above(float p, float thr, float avg, float snr) 
     return !(p < thr) && !(__fdiv_rn(p, avg) < snr);
 }
 
-// bin -> position inside one stored spectrogram column.  In the register kernel thread j of a half-warp
-// ends up with bins j + 16*k2 (k2 = 0..15) and stores them as four float4 (k2 = 4c..4c+3); the layout
-// pos = 64*(k2 >> 2) + 4*j + (k2 & 3) makes each of those four store instructions lane-contiguous
-// (256 B per half-warp), i.e. fully coalesced.
-template <bool PERM>
-__device__ __forceinline__ int bin_pos(int fi) {
-    return PERM ? (((fi >> 6) << 6) | ((fi & 15) << 2) | ((fi >> 4) & 3)) : fi;
-}
+// Spectrogram layouts.
+//   LINEAR (generic kernel)        S[stream][t][bin]
+//   PERM   (register kernel v7)    S[stream][t][pos(bin)], pos = 64 (k2 >> 2) + 4 k1 + (k2 & 3) for bin = k1 + 16 k2: thread k1 of a
+//                                  half-warp stores its bins as four float4, each store instruction 256 contiguous bytes
+//   TILE   (tensor-core kernel)    S[stream][t / 32][quad][t % 32][4], quad = 4 k1 + (k2 >> 2) (rt::tile_cell_off): a thread owns a
+//                                  segment, a warp stores 512 contiguous bytes, 32 time steps of a bin lie within 512 bytes
+enum { LAYOUT_LINEAR = 0, LAYOUT_PERM = 1, LAYOUT_TILE = 2 };
+
+struct CellRef {
+    const float* base;     // stream base + the bin's constant part
+    int step;              // LINEAR / PERM: floats per time step
+    template <int L>
+    __device__ __forceinline__ static CellRef make(const float* S, size_t stream_stride, int s, int fi, int n) {
+        CellRef c;
+        if (L == LAYOUT_TILE) { c.base = S + (size_t)s * stream_stride + (size_t)((fi & 15) * 4 + (fi >> 6)) * 128 + ((fi >> 4) & 3); c.step = 0; }
+        else if (L == LAYOUT_PERM) { c.base = S + (size_t)s * stream_stride + (((fi >> 6) << 6) | ((fi & 15) << 2) | ((fi >> 4) & 3)); c.step = 256; }
+        else { c.base = S + (size_t)s * stream_stride + fi; c.step = n; }
+        return c;
+    }
+    template <int L>
+    __device__ __forceinline__ float at(int t) const {
+        return L == LAYOUT_TILE ? base[(size_t)(t >> 5) * 8192 + (size_t)(t & 31) * 4] : base[(size_t)t * step];
+    }
+};
 
 // ---------------------------------------------------------------------------------------------
 // spectrogram, generic: any power-of-two nperseg in [8, 4096]; Stockham radix-4 in shared memory
@@ -161,6 +181,7 @@ __global__ void __launch_bounds__(NT) spectro_generic(SpectroArgs a) {
     }
     float* pd = a.part + ((size_t)s * a.n_chunks + blockIdx.x) * n;
     for (int i = tid; i < n; i += NT) pd[i] = rowacc[i];
+    rt::finish_row_means(a, s, NT);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -186,8 +207,9 @@ __global__ void row_mean_kernel(const float* part, float* avg, int n, int n_chun
 // probe + extraction (analyze.py:354-447)
 // ---------------------------------------------------------------------------------------------
 struct ScanArgs {
-    const float* S;        // current block  [stream][T][n]
+    const float* S;        // current block (LINEAR or TILE layout)
     const float* Sprev;    // previous block
+    size_t stream_stride;  // floats per stream
     const float* avg;      // [stream][n]
     const float* thr;      // [stream]
     const int* has_prev;   // [stream]
@@ -202,23 +224,22 @@ struct ScanArgs {
 constexpr int PROBE_QUICK = 3;   // cells examined on each side before handing a probe hit to a warp
 constexpr int EX_W = 4;          // 32-cell windows an extraction warp examines per memory round trip
 
-template <bool PERM>
+template <int TILE>
 __global__ void probe_kernel(ScanArgs a) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= a.n_probes * a.n) return;
     const int k = idx / a.n, fi = idx - k * a.n;
     const int s = blockIdx.y;
     const int ti = k * a.stride;
-    const int pos = bin_pos<PERM>(fi);
-    const float* col = a.S + (size_t)s * a.T * a.n + pos;
+    const CellRef col = CellRef::make<TILE>(a.S, a.stream_stride, s, fi, a.n);
     const float thr = a.thr[s], avg = a.avg[s * a.n + fi], snr = a.snr;
     // the probe cell and its PROBE_QUICK neighbours on each side, loaded up front (one memory round trip)
     float lo_c[PROBE_QUICK], hi_c[PROBE_QUICK];
-    const float c0 = col[(size_t)ti * a.n];
+    const float c0 = col.at<TILE>(ti);
 #pragma unroll
     for (int d = 1; d <= PROBE_QUICK; ++d) {
-        lo_c[d - 1] = (ti - d >= 0) ? col[(size_t)(ti - d) * a.n] : 0.f;
-        hi_c[d - 1] = (ti + d < a.T) ? col[(size_t)(ti + d) * a.n] : 0.f;
+        lo_c[d - 1] = (ti - d >= 0) ? col.at<TILE>(ti - d) : 0.f;
+        hi_c[d - 1] = (ti + d < a.T) ? col.at<TILE>(ti + d) : 0.f;
     }
     if (!above(c0, thr, avg, snr)) return;
 
@@ -252,7 +273,7 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-template <bool PERM>
+template <int TILE>
 __global__ void extract_kernel(ScanArgs a) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -263,9 +284,8 @@ __global__ void extract_kernel(ScanArgs a) {
     for (int item = warp; item < n_work; item += n_warps) {
         const uint2 wk = a.work[item];
         const int s = wk.x >> 16, fi = wk.x & 0xffff, ti = (int)wk.y;
-        const int pos = bin_pos<PERM>(fi);
-        const float* col = a.S + (size_t)s * T * n + pos;
-        const float* pcol = a.Sprev + (size_t)s * T * n + pos;
+        const CellRef col = CellRef::make<TILE>(a.S, a.stream_stride, s, fi, n);
+        const CellRef pcol = CellRef::make<TILE>(a.Sprev, a.stream_stride, s, fi, n);
         const float thr = a.thr[s], avg = a.avg[s * n + fi], snr = a.snr;
 
         // ---- backward: nearest not-above cell in [ti - stride, ti).  If there is none and the
@@ -279,7 +299,7 @@ __global__ void extract_kernel(ScanArgs a) {
             for (int w = 0; w < EX_W; ++w) {
                 const int t = base - 32 * w - lane;
                 const bool valid = t >= lo_lim;
-                const float p = valid ? col[(size_t)t * n] : 0.f;
+                const float p = valid ? col.at<TILE>(t) : 0.f;
                 m[w] = __ballot_sync(0xffffffffu, valid && !above(p, thr, avg, snr));
             }
 #pragma unroll
@@ -305,7 +325,7 @@ __global__ void extract_kernel(ScanArgs a) {
                 for (int w = 0; w < EX_W; ++w) {
                     const int jj = base + 32 * w + lane;
                     const bool valid = jj <= jcap;
-                    const float p = valid ? pcol[(size_t)(T - jj) * n] : 0.f;
+                    const float p = valid ? pcol.at<TILE>(T - jj) : 0.f;
                     m[w] = __ballot_sync(0xffffffffu, valid && !above(p, thr, avg, snr));
                 }
 #pragma unroll
@@ -328,7 +348,7 @@ __global__ void extract_kernel(ScanArgs a) {
             for (int w = 0; w < EX_W; ++w) {
                 const int t = base + 32 * w + lane;
                 const bool valid = t < T;
-                const float p = valid ? col[(size_t)t * n] : 0.f;
+                const float p = valid ? col.at<TILE>(t) : 0.f;
                 m[w] = __ballot_sync(0xffffffffu, valid && !above(p, thr, avg, snr));
             }
 #pragma unroll
@@ -348,7 +368,7 @@ __global__ void extract_kernel(ScanArgs a) {
 #pragma unroll
             for (int w = 0; w < EX_W; ++w) {
                 const int i = i0 + 32 * w;
-                pv[w] = i >= end ? -1.f : (i < 0 ? pcol[(size_t)(T + i) * n] : col[(size_t)i * n]);
+                pv[w] = i >= end ? -1.f : (i < 0 ? pcol.at<TILE>(T + i) : col.at<TILE>(i));
             }
 #pragma unroll
             for (int w = 0; w < EX_W; ++w)
@@ -380,12 +400,13 @@ __global__ void extract_kernel(ScanArgs a) {
     }
 }
 
-// un-permute one stored column set for the parity hook
-__global__ void unpermute_kernel(const float* S, float* out, int T, int total) {
+// PERM / TILE -> [T][256] for the parity hook, with the power scale of the tensor-core path undone (a power of two: exact)
+template <int L>
+__global__ void untile_kernel(const float* S, float* out, int total, float inv_scale) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int t = idx >> 8, fi = idx & 255;
-    out[idx] = S[(size_t)t * 256 + bin_pos<true>(fi)];
+    out[idx] = CellRef::make<L>(S, 0, 0, fi, 256).at<L>(t) * inv_scale;
 }
 
 }  // namespace
@@ -399,13 +420,24 @@ struct rt_engine {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int n = 0, T = 0, n_streams = 0, n_chunks = 0, chunk_segs = 0, n_probes = 0;
-    bool reg256 = false;
+    bool reg256 = false;                     // nperseg 256: register kernel (v7) or tensor-core kernel; TILE layout
+    bool tc256 = false;                      // tensor-core stage 1 (spectro_tc256.cuh)
+    size_t s_stride = 0;                     // floats per stream in a spectrogram buffer
+    float pscale = 1.f;                      // power factor carried by S / row means / thresholds (tensor-core path), a power of two
+    uint4* d_bmat = nullptr;                 // tensor-core operand image
+    rt::TcTables tc_tab;
+    int tc_grid = 0, tc_slots = 1, tc_bps = 0;
     float* d_win = nullptr;
     float2* d_tw = nullptr;
-    float* d_S[2] = {nullptr, nullptr};
+    // three spectrogram buffers: launch i writes S[i % 3] while the scan of launch i-1 still reads
+    // S[(i-1) % 3] (its block) and S[(i-2) % 3] (its carry) on the scan stream
+    float* d_S[RT_SBUFS] = {nullptr, nullptr, nullptr};
     int cur = 0;
-    float* d_part = nullptr;
-    float* d_avg = nullptr;
+    float* d_part[2] = {nullptr, nullptr};   // chunk row sums, by launch parity
+    cudaStream_t scan_stream = nullptr;      // row mean / probe / extract: overlaps the next launch's spectrogram
+    cudaEvent_t spec_done[2] = {nullptr, nullptr};
+    float* d_avg[2] = {nullptr, nullptr};    // row means, by launch parity (written by the spectrogram kernel)
+    unsigned* d_ctr = nullptr;               // [n_streams] finished-CTA tickets of the spectrogram kernel
     float* d_thr = nullptr;
     int* d_hasprev = nullptr;
     std::vector<int> h_hasprev;
@@ -425,7 +457,7 @@ struct rt_engine {
     bool launched = false;
     // timing
     bool timing = false;
-    struct EvSet { cudaEvent_t ev[5]; };
+    struct EvSet { cudaEvent_t ev[6]; };   // launch stream: before / after spectrogram; scan stream: start, row mean, probe, extract
     std::vector<EvSet> ev_pool;
     size_t ev_used = 0;
     rt_timing acc{};
@@ -436,9 +468,11 @@ namespace {
 int harvest_timing(rt_engine* e) {
     if (e->ev_used == 0) return RT_OK;
     CU(cudaStreamSynchronize(e->stream));
+    if (e->scan_stream) CU(cudaStreamSynchronize(e->scan_stream));
     for (size_t i = 0; i < e->ev_used; ++i) {
         float ms[4];
-        for (int k = 0; k < 4; ++k) CU(cudaEventElapsedTime(&ms[k], e->ev_pool[i].ev[k], e->ev_pool[i].ev[k + 1]));
+        CU(cudaEventElapsedTime(&ms[0], e->ev_pool[i].ev[0], e->ev_pool[i].ev[1]));
+        for (int k = 1; k < 4; ++k) CU(cudaEventElapsedTime(&ms[k], e->ev_pool[i].ev[k + 1], e->ev_pool[i].ev[k + 2]));
         e->acc.spectrogram_ms += ms[0];
         e->acc.rowmean_ms += ms[1];
         e->acc.probe_ms += ms[2];
@@ -452,13 +486,17 @@ void free_engine(rt_engine* e) {
     if (!e) return;
     cudaSetDevice(e->dev);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->scan_stream) cudaStreamSynchronize(e->scan_stream);
     for (auto& s : e->ev_pool)
         for (auto& ev : s.ev) cudaEventDestroy(ev);
-    cudaFree(e->d_win); cudaFree(e->d_tw); cudaFree(e->d_S[0]); cudaFree(e->d_S[1]);
-    cudaFree(e->d_part); cudaFree(e->d_avg); cudaFree(e->d_thr); cudaFree(e->d_hasprev);
+    cudaFree(e->d_win); cudaFree(e->d_tw);
+    for (auto& p : e->d_S) cudaFree(p);
+    cudaFree(e->d_part[0]); cudaFree(e->d_part[1]); cudaFree(e->d_avg[0]); cudaFree(e->d_avg[1]); cudaFree(e->d_ctr); cudaFree(e->d_bmat); cudaFree(e->d_thr); cudaFree(e->d_hasprev);
     cudaFree(e->d_stage); cudaFree(e->d_work); cudaFree(e->d_counters); cudaFree(e->d_rec[0]); cudaFree(e->d_rec[1]); cudaFree(e->d_tmp);
     for (auto& ev : e->done) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : e->spec_done) if (ev) cudaEventDestroy(ev);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->scan_stream) cudaStreamDestroy(e->scan_stream);
     if (e->h_rec) cudaFreeHost(e->h_rec);
     if (e->h_counters) cudaFreeHost(e->h_counters);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
@@ -498,7 +536,7 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     if (cfg->cuda_device < 0 || cfg->cuda_device >= ndev) return fail(RT_ERR_CUDA, "no such CUDA device (this engine has no CPU fallback)");
     CU(cudaSetDevice(cfg->cuda_device));
     cudaFuncAttributes fa;
-    cudaError_t ferr = cudaFuncGetAttributes(&fa, row_mean_kernel);
+    cudaError_t ferr = cudaFuncGetAttributes(&fa, probe_kernel<LAYOUT_PERM>);
     if (ferr != cudaSuccess)
         return fail(RT_ERR_CUDA, std::string("kernels not loadable on this device (built for sm_100a only): ") + cudaGetErrorString(ferr));
 
@@ -509,10 +547,13 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     e->T = (int)(cfg->block_samples / n);
     e->n_streams = cfg->n_streams;
     e->n_probes = (e->T + cfg->probe_stride - 1) / cfg->probe_stride;
-    if (cfg->fft_impl == RT_FFT_REG256 && n != 256) { delete e; return fail(RT_ERR_INVALID, "RT_FFT_REG256 needs nperseg == 256"); }
+    if ((cfg->fft_impl == RT_FFT_REG256 || cfg->fft_impl == RT_FFT_TC256) && n != 256) { delete e; return fail(RT_ERR_INVALID, "RT_FFT_REG256 / RT_FFT_TC256 need nperseg == 256"); }
+    if (cfg->fft_impl < RT_FFT_AUTO || cfg->fft_impl > RT_FFT_TC256) { delete e; return fail(RT_ERR_INVALID, "unknown fft_impl"); }
     e->reg256 = (n == 256) && (cfg->fft_impl != RT_FFT_GENERIC);
+    e->tc256 = cfg->fft_impl == RT_FFT_TC256;
     e->chunk_segs = e->reg256 ? 256 : 32;
     e->n_chunks = (e->T + e->chunk_segs - 1) / e->chunk_segs;
+    e->s_stride = e->tc256 ? (size_t)((e->T + 31) / 32) * 8192 : (size_t)e->T * n;
 
 #define CUE(call)                                                                                  \
     do {                                                                                           \
@@ -534,22 +575,46 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     const double amp = std::sqrt(1.0 / (cfg->sample_rate * sw2)) / 127.5;
     std::vector<float> hwin(n);
     for (int i = 0; i < n; ++i) hwin[i] = (float)(cfg->window[i] * amp);
+    if (e->tc256) {
+        e->tc_tab = rt::tc_make_tables(cfg->window, amp);
+        if (!e->tc_tab.eligible) { free_engine(e); return fail(RT_ERR_INVALID, "RT_FFT_TC256 needs a window whose DFT is confined to the bins 0 and +-1 (boxcar, hann, hamming)"); }
+        e->pscale = e->tc_tab.pscale;
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->dev) != cudaSuccess || sms < 1) sms = 148;
+        constexpr int NG = 2;
+        e->tc_bps = (e->T + rt::Tc256<NG>::BATCH - 1) / rt::Tc256<NG>::BATCH;
+        const long long Btot = (long long)e->n_streams * e->tc_bps;
+        e->tc_grid = (int)std::max<long long>(1, std::min<long long>(sms, Btot / NG));
+        const long long G = (long long)e->tc_grid * NG;
+        for (int s = 0; s < e->n_streams; ++s)
+            e->tc_slots = std::max(e->tc_slots, rt::tc_last_run(s, e->tc_bps, G, Btot) - rt::tc_first_run(s, e->tc_bps, G, Btot) + 1);
+    }
     std::vector<float2> htw(n);
     for (int k = 0; k < n; ++k) {
         const double ang = -2.0 * M_PI * (double)k / (double)n;
         htw[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
     }
     std::vector<float> hthr(e->n_streams);
-    for (int s = 0; s < e->n_streams; ++s) hthr[s] = (float)cfg->signal_threshold[s];
+    for (int s = 0; s < e->n_streams; ++s) hthr[s] = (float)cfg->signal_threshold[s] * e->pscale;   // pscale is a power of two: exact
 
-    const size_t cells = (size_t)e->n_streams * e->T * n;
+    const size_t cells = (size_t)e->n_streams * e->s_stride;
+    const size_t part_rows = e->tc256 ? (size_t)e->tc_slots : (size_t)e->n_chunks;
     const size_t max_work = (size_t)e->n_streams * n * e->n_probes;
     CUE(cudaMalloc(&e->d_win, n * sizeof(float)));
     CUE(cudaMalloc(&e->d_tw, n * sizeof(float2)));
-    CUE(cudaMalloc(&e->d_S[0], cells * sizeof(float)));
-    CUE(cudaMalloc(&e->d_S[1], cells * sizeof(float)));
-    CUE(cudaMalloc(&e->d_part, (size_t)e->n_streams * e->n_chunks * n * sizeof(float)));
-    CUE(cudaMalloc(&e->d_avg, (size_t)e->n_streams * n * sizeof(float)));
+    for (int k = 0; k < RT_SBUFS; ++k) CUE(cudaMalloc(&e->d_S[k], cells * sizeof(float)));
+    for (int k = 0; k < 2; ++k) {
+        CUE(cudaMalloc(&e->d_part[k], (size_t)e->n_streams * part_rows * n * sizeof(float)));
+        CUE(cudaMemset(e->d_part[k], 0, (size_t)e->n_streams * part_rows * n * sizeof(float)));
+    }
+    if (e->tc256) {
+        CUE(cudaMalloc(&e->d_bmat, e->tc_tab.bmat.size() * sizeof(uint16_t)));
+        CUE(cudaMemcpy(e->d_bmat, e->tc_tab.bmat.data(), e->tc_tab.bmat.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        CUE(cudaFuncSetAttribute(rt::spectro_tc256_k<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::Tc256<2>::SMEM));
+    }
+    for (int k = 0; k < 2; ++k) CUE(cudaMalloc(&e->d_avg[k], (size_t)e->n_streams * n * sizeof(float)));
+    CUE(cudaMalloc(&e->d_ctr, e->n_streams * sizeof(unsigned)));
+    CUE(cudaMemset(e->d_ctr, 0, e->n_streams * sizeof(unsigned)));
     CUE(cudaMalloc(&e->d_thr, e->n_streams * sizeof(float)));
     CUE(cudaMalloc(&e->d_hasprev, e->n_streams * sizeof(int)));
     CUE(cudaMalloc(&e->d_work, max_work * sizeof(uint2)));
@@ -557,8 +622,16 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     for (int k = 0; k < RT_SLOTS; ++k) {
         CUE(cudaMalloc(&e->d_rec[k], (size_t)cfg->max_records * sizeof(rt_record)));
         CUE(cudaEventCreateWithFlags(&e->done[k], cudaEventDisableTiming));
+        CUE(cudaEventCreateWithFlags(&e->spec_done[k], cudaEventDisableTiming));
     }
     CUE(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    const char* ov = std::getenv("RT_SCAN_OVERLAP");     // "0": run the scan kernels on the launch stream (no overlap)
+    if (!(ov && ov[0] == '0')) {
+        // the scan kernels are small and latency bound: give them priority over the next launch's spectrogram CTAs
+        int prio_lo = 0, prio_hi = 0;
+        CUE(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUE(cudaStreamCreateWithPriority(&e->scan_stream, cudaStreamNonBlocking, prio_hi));
+    }
     CUE(cudaMallocHost(&e->h_rec, (size_t)cfg->max_records * sizeof(rt_record)));
     CUE(cudaMallocHost(&e->h_counters, 2 * sizeof(int)));
     CUE(cudaMemcpy(e->d_win, hwin.data(), n * sizeof(float), cudaMemcpyHostToDevice));
@@ -584,6 +657,7 @@ int rt_engine_set_stream(rt_engine* e, void* cuda_stream) {
     if (!e) return fail(RT_ERR_INVALID, "null engine");
     CU(cudaSetDevice(e->dev));
     CU(cudaStreamSynchronize(e->stream));
+    if (e->scan_stream) CU(cudaStreamSynchronize(e->scan_stream));
     if (e->own_stream) {
         CU(cudaStreamDestroy(e->stream));
         e->own_stream = false;
@@ -626,14 +700,14 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
         d_iq = e->d_stage;
         stride = e->stage_stride;
     }
-    if (e->hasprev_dirty) {
-        CU(cudaMemcpyAsync(e->d_hasprev, e->h_hasprev.data(), e->n_streams * sizeof(int), cudaMemcpyHostToDevice, st));
-        e->hasprev_dirty = false;
-    }
     const int slot = (int)(e->launch_seq % RT_SLOTS);
     if (e->launch_seq - e->fetch_seq == RT_SLOTS) e->fetch_seq++;      // ring full: the oldest unfetched result is dropped
     int* d_cnt = e->d_counters + 2 * slot;
-    CU(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), st));
+    cudaStream_t sc_st = e->scan_stream ? e->scan_stream : st;
+    // Two streams: the spectrogram of this launch runs on the launch stream while the scan kernels of the
+    // previous launch are still busy on the scan stream.  The buffers this launch writes (S[next], part[slot])
+    // were last read by the scan of launch i-2, whose completion event is done[slot].
+    if (e->launch_seq >= RT_SLOTS && e->scan_stream) CU(cudaStreamWaitEvent(st, e->done[slot], 0));
 
     rt_engine::EvSet* evs = nullptr;
     if (e->timing) {
@@ -649,16 +723,27 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
         CU(cudaEventRecord(evs->ev[0], st));
     }
 
-    const int next = e->cur ^ 1;
+    const int next = (e->cur + 1) % RT_SBUFS;
     SpectroArgs sa;
     sa.iq = d_iq; sa.stream_stride = stride; sa.n = e->n; sa.T = e->T;
     sa.chunk_segs = e->chunk_segs; sa.n_chunks = e->n_chunks;
-    sa.win = e->d_win; sa.tw = e->d_tw; sa.S = e->d_S[next]; sa.part = e->d_part;
+    sa.win = e->d_win; sa.tw = e->d_tw; sa.S = e->d_S[next]; sa.part = e->d_part[slot];
+    sa.S_stream_stride = e->s_stride;
+    sa.avg = nullptr; sa.ctr = nullptr;          // row means: row_mean_kernel on the scan stream (the in-kernel variant costs the spectrogram ~10 us)
     const bool aligned = (((uintptr_t)d_iq | stride) & 15) == 0;
     const bool use_reg = e->reg256 && aligned;
     if (e->reg256 && !aligned) return fail(RT_ERR_INVALID, "register FFT path needs 16-byte aligned IQ and stream stride");
     dim3 grid(e->n_chunks, e->n_streams);
-    if (use_reg) {
+    if (use_reg && e->tc256) {
+        rt::TcArgs ta;
+        ta.iq = d_iq; ta.stream_stride = stride; ta.T = e->T; ta.n_streams = e->n_streams;
+        ta.bps = e->tc_bps; ta.total_batches = e->n_streams * e->tc_bps;
+        ta.bmat = e->d_bmat; ta.wc0 = e->tc_tab.wc0; ta.wc1 = e->tc_tab.wc1; ta.wc255 = e->tc_tab.wc255;
+        ta.S = e->d_S[next]; ta.S_stream_stride = e->s_stride;
+        ta.part = e->d_part[slot]; ta.part_slots = e->tc_slots; ta.avg = e->d_avg[slot]; ta.ctr = e->d_ctr;
+        ta.store = 1; ta.dbg = 0; ta.prof = nullptr;
+        rt::spectro_tc256_k<2><<<e->tc_grid, 512, rt::Tc256<2>::SMEM, st>>>(ta);
+    } else if (use_reg) {
         rt::spectro_reg256_v7<true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
     } else {
         const size_t smem = (size_t)e->n * (2 * sizeof(float2) + sizeof(float)) + 16;
@@ -666,35 +751,48 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     }
     CU(cudaGetLastError());
     if (evs) CU(cudaEventRecord(evs->ev[1], st));
+    if (e->scan_stream) CU(cudaEventRecord(e->spec_done[slot], st));
 
-    row_mean_kernel<<<dim3((e->n + 255) / 256, e->n_streams), 256, 0, st>>>(e->d_part, e->d_avg, e->n, e->n_chunks, e->T);
-    CU(cudaGetLastError());
-    if (evs) CU(cudaEventRecord(evs->ev[2], st));
+    // ---- scan stream: probe, extraction (in launch order; d_work / d_hasprev live here)
+    if (e->scan_stream) CU(cudaStreamWaitEvent(sc_st, e->spec_done[slot], 0));
+    if (e->hasprev_dirty) {
+        CU(cudaMemcpyAsync(e->d_hasprev, e->h_hasprev.data(), e->n_streams * sizeof(int), cudaMemcpyHostToDevice, sc_st));
+        e->hasprev_dirty = false;
+    }
+    CU(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), sc_st));
+    if (evs) CU(cudaEventRecord(evs->ev[2], sc_st));
+    if (!(use_reg && e->tc256)) {                          // the tensor-core kernel reduces its row sums itself
+        row_mean_kernel<<<dim3((e->n + 255) / 256, e->n_streams), 256, 0, sc_st>>>(e->d_part[slot], e->d_avg[slot], e->n, e->n_chunks, e->T);
+        CU(cudaGetLastError());
+    }
+    if (evs) CU(cudaEventRecord(evs->ev[3], sc_st));
 
     ScanArgs sc;
-    sc.S = e->d_S[next]; sc.Sprev = e->d_S[e->cur]; sc.avg = e->d_avg; sc.thr = e->d_thr; sc.has_prev = e->d_hasprev;
+    sc.S = e->d_S[next]; sc.Sprev = e->d_S[e->cur]; sc.stream_stride = e->s_stride; sc.avg = e->d_avg[slot]; sc.thr = e->d_thr; sc.has_prev = e->d_hasprev;
     sc.snr = (float)e->cfg.snr_threshold;
     sc.n = e->n; sc.T = e->T; sc.stride = e->cfg.probe_stride; sc.n_probes = e->n_probes;
     sc.min_cols = e->cfg.min_cols; sc.max_cols = e->cfg.max_cols;
     sc.work = e->d_work; sc.counters = d_cnt; sc.rec = e->d_rec[slot]; sc.max_records = e->cfg.max_records;
     dim3 pgrid((e->n_probes * e->n + 255) / 256, e->n_streams);
-    if (use_reg) probe_kernel<true><<<pgrid, 256, 0, st>>>(sc);
-    else probe_kernel<false><<<pgrid, 256, 0, st>>>(sc);
+    if (use_reg && e->tc256) probe_kernel<LAYOUT_TILE><<<pgrid, 256, 0, sc_st>>>(sc);
+    else if (use_reg) probe_kernel<LAYOUT_PERM><<<pgrid, 256, 0, sc_st>>>(sc);
+    else probe_kernel<LAYOUT_LINEAR><<<pgrid, 256, 0, sc_st>>>(sc);
     CU(cudaGetLastError());
-    if (evs) CU(cudaEventRecord(evs->ev[3], st));
-    if (use_reg) extract_kernel<true><<<148 * 8, 256, 0, st>>>(sc);
-    else extract_kernel<false><<<148 * 8, 256, 0, st>>>(sc);
+    if (evs) CU(cudaEventRecord(evs->ev[4], sc_st));
+    if (use_reg && e->tc256) extract_kernel<LAYOUT_TILE><<<148 * 8, 256, 0, sc_st>>>(sc);
+    else if (use_reg) extract_kernel<LAYOUT_PERM><<<148 * 8, 256, 0, sc_st>>>(sc);
+    else extract_kernel<LAYOUT_LINEAR><<<148 * 8, 256, 0, sc_st>>>(sc);
     CU(cudaGetLastError());
-    if (evs) CU(cudaEventRecord(evs->ev[4], st));
+    if (evs) CU(cudaEventRecord(evs->ev[5], sc_st));
 
-    CU(cudaEventRecord(e->done[slot], st));
+    CU(cudaEventRecord(e->done[slot], sc_st));
     e->launch_seq++;
     e->cur = next;
     for (auto& h : e->h_hasprev)
         if (!h) { h = 1; e->hasprev_dirty = true; }
     e->launched = true;
     e->acc.launches += 1;
-    e->acc.kernels += 4;
+    e->acc.kernels += (use_reg && e->tc256) ? 3 : 4;
     return RT_OK;
 }
 
@@ -720,8 +818,24 @@ int rt_engine_fetch(rt_engine* e, rt_record* out, int32_t max_out, int32_t* n_ou
             if (x.fi != y.fi) return x.fi < y.fi;
             return x.start < y.start;
         });
+        if (e->pscale != 1.f) {
+            const float inv = 1.f / e->pscale;           // power of two: exact
+            for (int i = 0; i < nrec; ++i) {
+                e->h_rec[i].max_lin *= inv;
+                e->h_rec[i].row_mean *= inv;
+                e->h_rec[i].mean_lin *= (double)inv;
+            }
+        }
         std::memcpy(out, e->h_rec, (size_t)nrec * sizeof(rt_record));
     }
+    return RT_OK;
+}
+
+int rt_engine_join(rt_engine* e) {
+    if (!e) return fail(RT_ERR_INVALID, "null engine");
+    if (e->launch_seq == 0 || !e->scan_stream) return RT_OK;
+    CU(cudaSetDevice(e->dev));
+    CU(cudaStreamWaitEvent(e->stream, e->done[(int)((e->launch_seq - 1) % RT_SLOTS)], 0));
     return RT_OK;
 }
 
@@ -737,11 +851,13 @@ int rt_engine_read_spectrogram(rt_engine* e, int32_t stream, float* out) {
     if (!e->launched) return fail(RT_ERR_STATE, "no launch yet");
     CU(cudaSetDevice(e->dev));
     const size_t cells = (size_t)e->T * e->n;
-    const float* src = e->d_S[e->cur] + (size_t)stream * cells;
+    const float* src = e->d_S[e->cur] + (size_t)stream * e->s_stride;
     CU(cudaStreamSynchronize(e->stream));
+    if (e->scan_stream) CU(cudaStreamSynchronize(e->scan_stream));
     if (e->reg256) {
         if (!e->d_tmp) CU(cudaMalloc(&e->d_tmp, cells * sizeof(float)));
-        unpermute_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, e->stream>>>(src, e->d_tmp, e->T, (int)cells);
+        if (e->tc256) untile_kernel<LAYOUT_TILE><<<(unsigned)((cells + 255) / 256), 256, 0, e->stream>>>(src, e->d_tmp, (int)cells, 1.f / e->pscale);
+        else untile_kernel<LAYOUT_PERM><<<(unsigned)((cells + 255) / 256), 256, 0, e->stream>>>(src, e->d_tmp, (int)cells, 1.f);
         CU(cudaGetLastError());
         src = e->d_tmp;
     }
@@ -754,8 +870,10 @@ int rt_engine_read_row_means(rt_engine* e, int32_t stream, float* out) {
     if (!e || !out || stream < 0 || stream >= e->n_streams) return fail(RT_ERR_INVALID, "bad argument");
     if (!e->launched) return fail(RT_ERR_STATE, "no launch yet");
     CU(cudaSetDevice(e->dev));
-    CU(cudaMemcpyAsync(out, e->d_avg + (size_t)stream * e->n, e->n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(out, e->d_avg[(int)((e->launch_seq - 1) % RT_SLOTS)] + (size_t)stream * e->n, e->n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
+    if (e->pscale != 1.f)
+        for (int i = 0; i < e->n; ++i) out[i] *= 1.f / e->pscale;
     return RT_OK;
 }
 

@@ -14,14 +14,14 @@ from . import build as _build
 
 RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_OVERFLOW, RT_ERR_STATE = 0, -1, -2, -3, -4
 RT_ABI_VERSION = 1
-FFT_AUTO, FFT_GENERIC, FFT_REG256 = 0, 1, 2
+FFT_AUTO, FFT_GENERIC, FFT_REG256, FFT_TC256 = 0, 1, 2, 3
 
 # every symbol include/rt_engine.h declares
 EXPORTS = (
     "rt_last_error", "rt_abi_version", "rt_device_count", "rt_engine_create", "rt_engine_destroy",
     "rt_engine_set_stream", "rt_engine_reset_stream", "rt_engine_process", "rt_engine_launch", "rt_engine_fetch",
     "rt_engine_shape", "rt_engine_read_spectrogram", "rt_engine_read_row_means", "rt_engine_enable_timing",
-    "rt_engine_get_timing",
+    "rt_engine_get_timing", "rt_engine_join",
 )
 
 
@@ -82,6 +82,7 @@ def load_library() -> ctypes.CDLL:
                                       ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
     lib.rt_engine_launch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_size_t]
     lib.rt_engine_fetch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
+    lib.rt_engine_join.argtypes = [ctypes.c_void_p]
     lib.rt_engine_shape.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int32)] * 3
     lib.rt_engine_read_spectrogram.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]
     lib.rt_engine_read_row_means.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]
@@ -204,6 +205,11 @@ class Engine:
 
     def set_stream(self, cuda_stream: int) -> None:
         _check(self._lib.rt_engine_set_stream(self._h, ctypes.c_void_p(cuda_stream)))
+
+    def join(self) -> None:
+        """Make the launch stream wait for the scan kernels of every launch so far (they run on an
+        engine-internal stream, overlapping the next launch's spectrogram)."""
+        _check(self._lib.rt_engine_join(self._h))
 
     # -- parity hooks / timing ------------------------------------------------------------------
     def read_spectrogram(self, stream: int = 0) -> np.ndarray:

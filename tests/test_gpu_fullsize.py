@@ -108,6 +108,34 @@ def test_both_fft_kernels_find_the_same_runs(batch, full_records):
         gen.close()
 
 
+def test_tensor_core_kernel_finds_the_same_runs(batch, full_records):
+    """RT_FFT_TC256 (tcgen05 stage 1, TMEM accumulators) against the register kernel at BASELINE configs[1] size."""
+    distinct, _ = batch
+    recs, spec, rm = full_records
+    tc = BatchAnalyzer(**_kwargs(N_DISTINCT, fft_impl=E.FFT_TC256))
+    try:
+        for b in range(N_BLOCKS):
+            g = tc.engine.process(np.stack([d[b] for d in distinct]))
+            for s in range(N_DISTINCT):
+                a, c = _strip(recs[b], s), _strip(g, s)
+                ka = {(int(x["fi"]), int(x["start"]), int(x["end"])) for x in a}
+                kc = {(int(x["fi"]), int(x["start"]), int(x["end"])) for x in c}
+                assert len(ka ^ kc) <= max(1, len(ka) // 100)      # fp32 rounding differs between the two FFTs
+                ia = {(int(x["fi"]), int(x["start"]), int(x["end"])): x for x in a}
+                ic = {(int(x["fi"]), int(x["start"]), int(x["end"])): x for x in c}
+                for k in sorted(ka & kc):
+                    assert abs(ia[k]["mean_lin"] / ic[k]["mean_lin"] - 1) < 1e-4
+                    assert abs(ia[k]["max_lin"] / ic[k]["max_lin"] - 1) < 1e-4
+        # last block, stream 5 == distinct[1]: cells and row means against the register kernel
+        got = tc.engine.read_spectrogram(5 % N_DISTINCT).astype(np.float64)
+        ref = spec.astype(np.float64)
+        big = ref >= 1e-3 * ref.max(axis=1, keepdims=True)
+        assert np.max(np.abs(got[big] - ref[big]) / ref[big]) < 2e-4
+        assert np.max(np.abs(tc.engine.read_row_means(5 % N_DISTINCT).astype(np.float64) / rm.astype(np.float64) - 1)) < 1e-5
+    finally:
+        tc.close()
+
+
 def test_parseval_on_full_size_columns(batch, full_records):
     distinct, _ = batch
     _, spec, _ = full_records                       # stream 5 == distinct[1], last block

@@ -15,8 +15,13 @@ from tests import golden_io, parity
 pytestmark = pytest.mark.gpu
 
 
-def _impls(nperseg):
-    return [E.FFT_GENERIC, E.FFT_REG256] if nperseg == 256 else [E.FFT_GENERIC]
+def _impls(nperseg, window="hamming"):
+    if nperseg != 256:
+        return [E.FFT_GENERIC]
+    impls = [E.FFT_GENERIC, E.FFT_REG256]
+    if window in ("hamming", "hann", "boxcar"):      # windows whose DFT lives in the bins 0 and +-1
+        impls.append(E.FFT_TC256)                    # tensor-core stage 1 (tcgen05)
+    return impls
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: c.name)
@@ -26,7 +31,7 @@ def test_case_matches_oracle_and_fixture(case):
     cap = case.capture()
     assert sha256(cap) == g.meta["input_sha256"]
     P = parity.oracle_params(kw)
-    for impl in _impls(kw["fft_nperseg"]):
+    for impl in _impls(kw["fft_nperseg"], kw["fft_window"] if isinstance(kw["fft_window"], str) else None):
         ora = R.OracleAnalyzer(P)
         ba = BatchAnalyzer(**parity.batch_kwargs(kw, fft_impl=impl))
         try:
