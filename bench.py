@@ -307,7 +307,7 @@ def run_b200(args):
             "config": {"workload": "configs[1]: 64x2.4MS/s nperseg256 hamming -90dBW/5dB 8-40ms", "streams_per_gpu": S,
                        "block_samples": w.block_samples, "distinct_streams": min(N_DISTINCT, S),
                        "l2": "inputs larger than L2 (307 MB per step, 2 alternating blocks)",
-                       "records_per_step": n_rec, "fft_impl": args.fft_impl,
+                       "records_per_step": n_rec, "extract_work_items_per_step": eng.last_counts()[0], "fft_impl": args.fft_impl,
                        "scan_overlap": os.environ.get("RT_SCAN_OVERLAP", "1") != "0"},
             "clocks": clk,
             "e2e": None if args.profile else {

@@ -137,6 +137,9 @@ int rt_engine_fetch(rt_engine *e, rt_record *out, int32_t max_out, int32_t *n_ou
  */
 int rt_engine_join(rt_engine *e);
 
+/* Counters of the last fetched launch: probe hits handed to the extraction kernel, and records emitted. */
+int rt_engine_last_counts(rt_engine *e, int32_t *work_items, int32_t *records);
+
 /* Spectrogram geometry: *T = block_samples / nperseg columns per block. */
 int rt_engine_shape(const rt_engine *e, int32_t *n_streams, int32_t *nperseg, int32_t *T);
 

@@ -7,10 +7,10 @@
 //
 // Kernels (one launch each per engine call, all streams of the batch at once):
 //   spectro_*      uint8 IQ -> power cells S (fp32, layout per kernel) + row sums / row means
-//   row_mean       deterministic reduction of the chunk sums -> freq_avg[stream][bin] (the tensor-core
-//                  kernel does this itself in the last warp-group run of each stream)
-//   probe          one thread per (stream, bin, probe column k*stride): predicate test,
-//                  cheap pruning of short noise runs, survivors -> work list
+//   probe          prologue: deterministic reduction of the chunk sums -> freq_avg[stream][bin] (the tensor-core
+//                  kernel does this itself in the last warp-group run of each stream); then one thread per
+//                  (stream, bin, 8 probe columns k*stride): predicate test, cheap pruning of short noise runs,
+//                  survivors -> work list
 //   extract        one warp per work item: run limits by ballot, carry into the
 //                  previous block, coarse duration gate, statistics, record emission
 //
@@ -181,26 +181,24 @@ __global__ void __launch_bounds__(NT) spectro_generic(SpectroArgs a) {
     }
     float* pd = a.part + ((size_t)s * a.n_chunks + blockIdx.x) * n;
     for (int i = tid; i < n; i += NT) pd[i] = rowacc[i];
-    rt::finish_row_means(a, s, NT);
 }
 
 // ---------------------------------------------------------------------------------------------
 // row means (analyze.py:374-375), deterministic
 // ---------------------------------------------------------------------------------------------
-__global__ void row_mean_kernel(const float* part, float* avg, int n, int n_chunks, int T) {
-    const int fi = blockIdx.x * blockDim.x + threadIdx.x;
-    const int s = blockIdx.y;
-    if (fi >= n) return;
+// fixed summation order (4 interleaved partial sums over the chunks), float64: run-to-run identical and
+// identical in every CTA that evaluates it
+__device__ __forceinline__ float row_mean_of(const float* part, int s, int fi, int n, int n_chunks, int T) {
     const float* p = part + (size_t)s * n_chunks * n + fi;
-    // fixed summation order (4 interleaved partial sums over the chunks), float64: run-to-run identical
-    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
-    int c = 0;
-    for (; c + 4 <= n_chunks; c += 4) {
-        const float a0 = p[(size_t)c * n], a1 = p[(size_t)(c + 1) * n], a2 = p[(size_t)(c + 2) * n], a3 = p[(size_t)(c + 3) * n];
-        t0 += (double)a0; t1 += (double)a1; t2 += (double)a2; t3 += (double)a3;
+    double t[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int c0 = 0; c0 < n_chunks; c0 += 16) {          // 16 chunk sums per memory round trip
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = (c0 + i < n_chunks) ? p[(size_t)(c0 + i) * n] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) t[i & 3] += (double)v[i];
     }
-    for (; c < n_chunks; ++c) t0 += (double)p[(size_t)c * n];
-    avg[s * n + fi] = (float)(((t0 + t1) + (t2 + t3)) / (double)T);
+    return (float)(((t[0] + t[1]) + (t[2] + t[3])) / (double)T);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -210,7 +208,9 @@ struct ScanArgs {
     const float* S;        // current block (LINEAR or TILE layout)
     const float* Sprev;    // previous block
     size_t stream_stride;  // floats per stream
-    const float* avg;      // [stream][n]
+    float* avg;            // [stream][n] row means: written by the probe kernel (from `part`) or by the tensor-core kernel
+    const float* part;     // [stream][n_chunks][n] chunk row sums (nullptr: avg is already there)
+    int n_chunks;
     const float* thr;      // [stream]
     const int* has_prev;   // [stream]
     float snr;
@@ -224,42 +224,66 @@ struct ScanArgs {
 constexpr int PROBE_QUICK = 3;   // cells examined on each side before handing a probe hit to a warp
 constexpr int EX_W = 4;          // 32-cell windows an extraction warp examines per memory round trip
 
+constexpr int PROBE_PPT = 8;     // probe columns per thread (their loads are in flight together)
+
+// One thread per (stream, bin, group of PROBE_PPT probe columns); blockDim.x bins of one stream per CTA.
+// Prologue: the bin's row mean from the chunk sums (analyze.py:374-375) -- every CTA of the stream computes the
+// same value, the CTAs of probe group 0 publish it for the extraction kernel and the parity hook.
 template <int TILE>
 __global__ void probe_kernel(ScanArgs a) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= a.n_probes * a.n) return;
-    const int k = idx / a.n, fi = idx - k * a.n;
+    const int nbb = (a.n + blockDim.x - 1) / blockDim.x;           // bin blocks
+    const int bb = blockIdx.x % nbb, g = blockIdx.x / nbb;
+    const int fi = bb * blockDim.x + threadIdx.x;
     const int s = blockIdx.y;
-    const int ti = k * a.stride;
+    if (fi >= a.n) return;
+    float avg;
+    if (a.part != nullptr) {
+        avg = row_mean_of(a.part, s, fi, a.n, a.n_chunks, a.T);
+        if (g == 0) a.avg[s * a.n + fi] = avg;
+    } else {
+        avg = a.avg[s * a.n + fi];
+    }
     const CellRef col = CellRef::make<TILE>(a.S, a.stream_stride, s, fi, a.n);
-    const float thr = a.thr[s], avg = a.avg[s * a.n + fi], snr = a.snr;
-    // the probe cell and its PROBE_QUICK neighbours on each side, loaded up front (one memory round trip)
-    float lo_c[PROBE_QUICK], hi_c[PROBE_QUICK];
-    const float c0 = col.at<TILE>(ti);
+    const float thr = a.thr[s], snr = a.snr;
+    // ~96 % of the probe cells fail the predicate: only a hit pays for its neighbours
+    float c0[PROBE_PPT];
 #pragma unroll
-    for (int d = 1; d <= PROBE_QUICK; ++d) {
-        lo_c[d - 1] = (ti - d >= 0) ? col.at<TILE>(ti - d) : 0.f;
-        hi_c[d - 1] = (ti + d < a.T) ? col.at<TILE>(ti + d) : 0.f;
+    for (int i = 0; i < PROBE_PPT; ++i) {
+        const int k = g * PROBE_PPT + i;
+        c0[i] = (k < a.n_probes) ? col.at<TILE>(k * a.stride) : 0.f;
     }
-    if (!above(c0, thr, avg, snr)) return;
-
-    // Most hits are 1-2 cell noise runs that the duration gate rejects anyway: resolve those here.
-    int lo = -1, hi = -1;             // nearest not-above cells, if found within PROBE_QUICK
+#pragma unroll 1
+    for (int i = 0; i < PROBE_PPT; ++i) {
+        const int k = g * PROBE_PPT + i;
+        if (k >= a.n_probes) break;
+        if (!above(c0[i], thr, avg, snr)) continue;
+        const int ti = k * a.stride;
+        float lo_c[PROBE_QUICK], hi_c[PROBE_QUICK];
 #pragma unroll
-    for (int d = 1; d <= PROBE_QUICK; ++d) {
-        const int t = ti - d;
-        if (t < 0) break;             // run reaches column 0: carry logic, leave it to the warp
-        if (!above(lo_c[d - 1], thr, avg, snr)) { lo = t; break; }
-    }
+        for (int d = 1; d <= PROBE_QUICK; ++d) {
+            lo_c[d - 1] = (ti - d >= 0) ? col.at<TILE>(ti - d) : 0.f;
+            hi_c[d - 1] = (ti + d < a.T) ? col.at<TILE>(ti + d) : 0.f;
+        }
+        // Most hits are 1-2 cell noise runs that the duration gate rejects anyway: resolve those here.
+        int lo = -1, hi = -1;             // nearest not-above cells, if found within PROBE_QUICK
+        bool drop = false;
 #pragma unroll
-    for (int d = 1; d <= PROBE_QUICK; ++d) {
-        const int t = ti + d;
-        if (t >= a.T) return;         // run touches the block end: dropped (analyze.py:415-417)
-        if (!above(hi_c[d - 1], thr, avg, snr)) { hi = t; break; }
+        for (int d = 1; d <= PROBE_QUICK; ++d) {
+            const int t = ti - d;
+            if (t < 0) break;             // run reaches column 0: carry logic, leave it to the warp
+            if (!above(lo_c[d - 1], thr, avg, snr)) { lo = t; break; }
+        }
+#pragma unroll
+        for (int d = 1; d <= PROBE_QUICK; ++d) {
+            const int t = ti + d;
+            if (t >= a.T) { drop = true; break; }     // run touches the block end: dropped (analyze.py:415-417)
+            if (!above(hi_c[d - 1], thr, avg, snr)) { hi = t; break; }
+        }
+        if (drop) continue;
+        if (lo >= 0 && hi >= 0 && hi - lo < a.min_cols) continue;   // window = [lo, hi): too short
+        const int slot = atomicAdd(&a.counters[0], 1);
+        a.work[slot] = make_uint2(((unsigned)s << 16) | (unsigned)fi, (unsigned)ti);
     }
-    if (lo >= 0 && hi >= 0 && hi - lo < a.min_cols) return;   // window = [lo, hi): too short
-    const int slot = atomicAdd(&a.counters[0], 1);
-    a.work[slot] = make_uint2(((unsigned)s << 16) | (unsigned)fi, (unsigned)ti);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -427,6 +451,7 @@ struct rt_engine {
     uint4* d_bmat = nullptr;                 // tensor-core operand image
     rt::TcTables tc_tab;
     int tc_grid = 0, tc_slots = 1, tc_bps = 0;
+    int probe_threads = 256, extract_threads = 256, extract_ctas = 148 * 8;   // scan launch shapes (RT_SCAN_SHAPE=probe,extract,ctas)
     float* d_win = nullptr;
     float2* d_tw = nullptr;
     // three spectrogram buffers: launch i writes S[i % 3] while the scan of launch i-1 still reads
@@ -442,8 +467,12 @@ struct rt_engine {
     int* d_hasprev = nullptr;
     std::vector<int> h_hasprev;
     bool hasprev_dirty = true;
-    uint8_t* d_stage = nullptr;
+    // host input: two staging buffers filled on an upload stream, so the copy of launch i+1 overlaps the kernels of launch i
+    uint8_t* d_stage[2] = {nullptr, nullptr};
     size_t stage_stride = 0;
+    cudaStream_t h2d_stream = nullptr;
+    cudaEvent_t h2d_done[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr};
+    unsigned long long h2d_seq = 0;
     uint2* d_work = nullptr;
     // results ring: up to RT_SLOTS launches may be in flight before their records are fetched
     int* d_counters = nullptr;              // [slot][2]
@@ -455,6 +484,7 @@ struct rt_engine {
     int* h_counters = nullptr;      // pinned
     float* d_tmp = nullptr;         // parity hook scratch
     bool launched = false;
+    int last_work_items = 0, last_records = 0;   // counters of the last fetched launch
     // timing
     bool timing = false;
     struct EvSet { cudaEvent_t ev[6]; };   // launch stream: before / after spectrogram; scan stream: start, row mean, probe, extract
@@ -492,7 +522,9 @@ void free_engine(rt_engine* e) {
     cudaFree(e->d_win); cudaFree(e->d_tw);
     for (auto& p : e->d_S) cudaFree(p);
     cudaFree(e->d_part[0]); cudaFree(e->d_part[1]); cudaFree(e->d_avg[0]); cudaFree(e->d_avg[1]); cudaFree(e->d_ctr); cudaFree(e->d_bmat); cudaFree(e->d_thr); cudaFree(e->d_hasprev);
-    cudaFree(e->d_stage); cudaFree(e->d_work); cudaFree(e->d_counters); cudaFree(e->d_rec[0]); cudaFree(e->d_rec[1]); cudaFree(e->d_tmp);
+    cudaFree(e->d_stage[0]); cudaFree(e->d_stage[1]); cudaFree(e->d_work);
+    for (int k = 0; k < 2; ++k) { if (e->h2d_done[k]) cudaEventDestroy(e->h2d_done[k]); if (e->stage_free[k]) cudaEventDestroy(e->stage_free[k]); }
+    if (e->h2d_stream) cudaStreamDestroy(e->h2d_stream); cudaFree(e->d_counters); cudaFree(e->d_rec[0]); cudaFree(e->d_rec[1]); cudaFree(e->d_tmp);
     for (auto& ev : e->done) if (ev) cudaEventDestroy(ev);
     for (auto& ev : e->spec_done) if (ev) cudaEventDestroy(ev);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -552,6 +584,11 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     e->reg256 = (n == 256) && (cfg->fft_impl != RT_FFT_GENERIC);
     e->tc256 = cfg->fft_impl == RT_FFT_TC256;
     e->chunk_segs = e->reg256 ? 256 : 32;
+    if (const char* cs = std::getenv("RT_CHUNK_SEGS")) { const int v = std::atoi(cs); if (e->reg256 && v >= 8 && v % 8 == 0) e->chunk_segs = v; }
+    if (const char* sh = std::getenv("RT_SCAN_SHAPE")) {
+        int a = 0, b = 0, c = 0;
+        if (std::sscanf(sh, "%d,%d,%d", &a, &b, &c) == 3 && a >= 32 && a <= 1024 && a % 32 == 0 && b >= 32 && b <= 1024 && b % 32 == 0 && c >= 1) { e->probe_threads = a; e->extract_threads = b; e->extract_ctas = c; }
+    }
     e->n_chunks = (e->T + e->chunk_segs - 1) / e->chunk_segs;
     e->s_stride = e->tc256 ? (size_t)((e->T + 31) / 32) * 8192 : (size_t)e->T * n;
 
@@ -630,7 +667,8 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
         // the scan kernels are small and latency bound: give them priority over the next launch's spectrogram CTAs
         int prio_lo = 0, prio_hi = 0;
         CUE(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        CUE(cudaStreamCreateWithPriority(&e->scan_stream, cudaStreamNonBlocking, prio_hi));
+        const char* pr = std::getenv("RT_SCAN_PRIO");                 // experiment: "lo" = same (lowest) priority as the launch stream
+        CUE(cudaStreamCreateWithPriority(&e->scan_stream, cudaStreamNonBlocking, (pr && pr[0] == 'l') ? prio_lo : prio_hi));
     }
     CUE(cudaMallocHost(&e->h_rec, (size_t)cfg->max_records * sizeof(rt_record)));
     CUE(cudaMallocHost(&e->h_counters, 2 * sizeof(int)));
@@ -691,13 +729,22 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     const uint8_t* d_iq = iq;
     size_t stride = stream_stride_bytes;
     if (!iq_on_device) {
-        if (!e->d_stage) {
+        if (!e->d_stage[0]) {
             e->stage_stride = (block_bytes + 255) & ~(size_t)255;
-            CU(cudaMalloc(&e->d_stage, e->stage_stride * e->n_streams));
+            for (int k = 0; k < 2; ++k) {
+                CU(cudaMalloc(&e->d_stage[k], e->stage_stride * e->n_streams));
+                CU(cudaEventCreateWithFlags(&e->h2d_done[k], cudaEventDisableTiming));
+                CU(cudaEventCreateWithFlags(&e->stage_free[k], cudaEventDisableTiming));
+            }
+            CU(cudaStreamCreateWithFlags(&e->h2d_stream, cudaStreamNonBlocking));
         }
-        CU(cudaMemcpy2DAsync(e->d_stage, e->stage_stride, iq, stream_stride_bytes, block_bytes, e->n_streams,
-                             cudaMemcpyHostToDevice, st));
-        d_iq = e->d_stage;
+        const int sb = (int)(e->h2d_seq & 1);
+        if (e->h2d_seq >= 2) CU(cudaStreamWaitEvent(e->h2d_stream, e->stage_free[sb], 0));   // the spectrogram kernel that read this buffer is done
+        CU(cudaMemcpy2DAsync(e->d_stage[sb], e->stage_stride, iq, stream_stride_bytes, block_bytes, e->n_streams,
+                             cudaMemcpyHostToDevice, e->h2d_stream));
+        CU(cudaEventRecord(e->h2d_done[sb], e->h2d_stream));
+        CU(cudaStreamWaitEvent(st, e->h2d_done[sb], 0));
+        d_iq = e->d_stage[sb];
         stride = e->stage_stride;
     }
     const int slot = (int)(e->launch_seq % RT_SLOTS);
@@ -729,7 +776,6 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     sa.chunk_segs = e->chunk_segs; sa.n_chunks = e->n_chunks;
     sa.win = e->d_win; sa.tw = e->d_tw; sa.S = e->d_S[next]; sa.part = e->d_part[slot];
     sa.S_stream_stride = e->s_stride;
-    sa.avg = nullptr; sa.ctr = nullptr;          // row means: row_mean_kernel on the scan stream (the in-kernel variant costs the spectrogram ~10 us)
     const bool aligned = (((uintptr_t)d_iq | stride) & 15) == 0;
     const bool use_reg = e->reg256 && aligned;
     if (e->reg256 && !aligned) return fail(RT_ERR_INVALID, "register FFT path needs 16-byte aligned IQ and stream stride");
@@ -752,6 +798,7 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     CU(cudaGetLastError());
     if (evs) CU(cudaEventRecord(evs->ev[1], st));
     if (e->scan_stream) CU(cudaEventRecord(e->spec_done[slot], st));
+    if (!iq_on_device) { CU(cudaEventRecord(e->stage_free[(int)(e->h2d_seq & 1)], st)); e->h2d_seq++; }
 
     // ---- scan stream: probe, extraction (in launch order; d_work / d_hasprev live here)
     if (e->scan_stream) CU(cudaStreamWaitEvent(sc_st, e->spec_done[slot], 0));
@@ -761,27 +808,25 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     }
     CU(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), sc_st));
     if (evs) CU(cudaEventRecord(evs->ev[2], sc_st));
-    if (!(use_reg && e->tc256)) {                          // the tensor-core kernel reduces its row sums itself
-        row_mean_kernel<<<dim3((e->n + 255) / 256, e->n_streams), 256, 0, sc_st>>>(e->d_part[slot], e->d_avg[slot], e->n, e->n_chunks, e->T);
-        CU(cudaGetLastError());
-    }
     if (evs) CU(cudaEventRecord(evs->ev[3], sc_st));
 
     ScanArgs sc;
-    sc.S = e->d_S[next]; sc.Sprev = e->d_S[e->cur]; sc.stream_stride = e->s_stride; sc.avg = e->d_avg[slot]; sc.thr = e->d_thr; sc.has_prev = e->d_hasprev;
+    sc.S = e->d_S[next]; sc.Sprev = e->d_S[e->cur]; sc.stream_stride = e->s_stride; sc.avg = e->d_avg[slot]; sc.part = (use_reg && e->tc256) ? nullptr : e->d_part[slot]; sc.n_chunks = e->n_chunks; sc.thr = e->d_thr; sc.has_prev = e->d_hasprev;
     sc.snr = (float)e->cfg.snr_threshold;
     sc.n = e->n; sc.T = e->T; sc.stride = e->cfg.probe_stride; sc.n_probes = e->n_probes;
     sc.min_cols = e->cfg.min_cols; sc.max_cols = e->cfg.max_cols;
     sc.work = e->d_work; sc.counters = d_cnt; sc.rec = e->d_rec[slot]; sc.max_records = e->cfg.max_records;
-    dim3 pgrid((e->n_probes * e->n + 255) / 256, e->n_streams);
-    if (use_reg && e->tc256) probe_kernel<LAYOUT_TILE><<<pgrid, 256, 0, sc_st>>>(sc);
-    else if (use_reg) probe_kernel<LAYOUT_PERM><<<pgrid, 256, 0, sc_st>>>(sc);
-    else probe_kernel<LAYOUT_LINEAR><<<pgrid, 256, 0, sc_st>>>(sc);
+    const int pth = e->probe_threads, eth = e->extract_threads, ect = e->extract_ctas;
+    const int pbins = std::min(e->n, pth);
+    dim3 pgrid(((e->n + pbins - 1) / pbins) * ((e->n_probes + PROBE_PPT - 1) / PROBE_PPT), e->n_streams);
+    if (use_reg && e->tc256) probe_kernel<LAYOUT_TILE><<<pgrid, pbins, 0, sc_st>>>(sc);
+    else if (use_reg) probe_kernel<LAYOUT_PERM><<<pgrid, pbins, 0, sc_st>>>(sc);
+    else probe_kernel<LAYOUT_LINEAR><<<pgrid, pbins, 0, sc_st>>>(sc);
     CU(cudaGetLastError());
     if (evs) CU(cudaEventRecord(evs->ev[4], sc_st));
-    if (use_reg && e->tc256) extract_kernel<LAYOUT_TILE><<<148 * 8, 256, 0, sc_st>>>(sc);
-    else if (use_reg) extract_kernel<LAYOUT_PERM><<<148 * 8, 256, 0, sc_st>>>(sc);
-    else extract_kernel<LAYOUT_LINEAR><<<148 * 8, 256, 0, sc_st>>>(sc);
+    if (use_reg && e->tc256) extract_kernel<LAYOUT_TILE><<<ect, eth, 0, sc_st>>>(sc);
+    else if (use_reg) extract_kernel<LAYOUT_PERM><<<ect, eth, 0, sc_st>>>(sc);
+    else extract_kernel<LAYOUT_LINEAR><<<ect, eth, 0, sc_st>>>(sc);
     CU(cudaGetLastError());
     if (evs) CU(cudaEventRecord(evs->ev[5], sc_st));
 
@@ -792,7 +837,7 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
         if (!h) { h = 1; e->hasprev_dirty = true; }
     e->launched = true;
     e->acc.launches += 1;
-    e->acc.kernels += (use_reg && e->tc256) ? 3 : 4;
+    e->acc.kernels += 3;
     return RT_OK;
 }
 
@@ -807,6 +852,8 @@ int rt_engine_fetch(rt_engine* e, rt_record* out, int32_t max_out, int32_t* n_ou
     CU(cudaMemcpyAsync(e->h_counters, e->d_counters + 2 * slot, 2 * sizeof(int), cudaMemcpyDeviceToHost, e->copy_stream));
     CU(cudaStreamSynchronize(e->copy_stream));
     const int nrec = e->h_counters[1];
+    e->last_work_items = e->h_counters[0];
+    e->last_records = nrec;
     *n_out = nrec;
     if (nrec > e->cfg.max_records) return fail(RT_ERR_OVERFLOW, "more candidate records than rt_config.max_records");
     if (nrec > max_out || (nrec > 0 && !out)) return fail(RT_ERR_OVERFLOW, "output buffer smaller than the number of records");
@@ -828,6 +875,13 @@ int rt_engine_fetch(rt_engine* e, rt_record* out, int32_t max_out, int32_t* n_ou
         }
         std::memcpy(out, e->h_rec, (size_t)nrec * sizeof(rt_record));
     }
+    return RT_OK;
+}
+
+int rt_engine_last_counts(rt_engine* e, int32_t* work_items, int32_t* records) {
+    if (!e) return fail(RT_ERR_INVALID, "null engine");
+    if (work_items) *work_items = e->last_work_items;
+    if (records) *records = e->last_records;
     return RT_OK;
 }
 

@@ -24,42 +24,7 @@ struct SpectroArgs {
     float* S;              // generic kernel: [stream][T][n]; register kernel: [stream][T][pos(bin)] (see rt_engine.cu)
     size_t S_stream_stride;  // floats per stream
     float* part;           // [stream][chunk][n]   (FFT bin order)
-    float* avg;            // [stream][n] row means, written by the last CTA of each stream (nullptr: skip)
-    unsigned* ctr;         // [stream] finished-CTA tickets (zero between launches)
 };
-
-// Row means (analyze.py:374-375): the CTA that finishes last for a stream reduces that stream's chunk sums,
-// always in the same order (four interleaved float64 partial sums over the chunks), so the result does not
-// depend on which CTA happens to be last.  Saves a separate launch behind the spectrogram kernel.
-__device__ __forceinline__ void finish_row_means(const SpectroArgs& a, int s, int n_threads) {
-    if (a.avg == nullptr) return;
-    __shared__ unsigned ticket;
-    __syncthreads();                               // every thread's chunk sums happen-before thread 0's fence
-    if (threadIdx.x == 0) {
-        // one cumulative fence instead of one per thread: a per-thread fence also waits for that thread's
-        // spectrogram stores to drain, which costs ~0.7 us at the end of every CTA
-        __threadfence();
-        ticket = atomicAdd(&a.ctr[s], 1u);
-    }
-    __syncthreads();
-    if (ticket != (unsigned)(a.n_chunks - 1)) return;
-    __threadfence();
-    const int n = a.n, n_chunks = a.n_chunks;
-    for (int fi = threadIdx.x; fi < n; fi += n_threads) {
-        const float* p = a.part + (size_t)s * n_chunks * n + fi;
-        double t[4] = {0.0, 0.0, 0.0, 0.0};
-        // 16 chunk sums per memory round trip; the additions keep the order t[c & 3] += part[c], c ascending
-        for (int c0 = 0; c0 < n_chunks; c0 += 16) {
-            float v[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = (c0 + i < n_chunks) ? __ldcg(p + (size_t)(c0 + i) * n) : 0.f;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) t[i & 3] += (double)v[i];
-        }
-        a.avg[(size_t)s * n + fi] = (float)(((t[0] + t[1]) + (t[2] + t[3])) / (double)a.T);
-    }
-    if (threadIdx.x == 0) a.ctr[s] = 0;             // ready for the next launch
-}
 
 // compile-time variant selection
 template <int STORE_, int NSEG_, int MINB_, int WARPS_, int STAGES_, bool WFOLD_, bool PACKACC_, int SUMS_, bool HINT_>
@@ -349,8 +314,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) spectro_reg256_k(SpectroA
 #pragma unroll
         for (int hh = 0; hh < 2 * C::WARPS; ++hh) t += red[hh * 256 + fi];
         pd[fi] = t;
-    }    finish_row_means(a, s, C::THREADS);
-}
+    }}
 
 // ---------------------------------------------------------------------------------------------
 // v7: same data flow as spectro_reg256_k<NSEG=1>, hand-tightened non-FMA instruction stream:
@@ -612,7 +576,6 @@ __global__ void __launch_bounds__(R256v7::THREADS, MINB) spectro_reg256_v7(Spect
 #pragma unroll
         for (int hh = 0; hh < 2 * C::WARPS; ++hh) t += red[hh * 256 + fi];
         pd[fi] = t;
-    }    finish_row_means(a, s, C::THREADS);
-}
+    }}
 
 }  // namespace rt

@@ -21,7 +21,7 @@ EXPORTS = (
     "rt_last_error", "rt_abi_version", "rt_device_count", "rt_engine_create", "rt_engine_destroy",
     "rt_engine_set_stream", "rt_engine_reset_stream", "rt_engine_process", "rt_engine_launch", "rt_engine_fetch",
     "rt_engine_shape", "rt_engine_read_spectrogram", "rt_engine_read_row_means", "rt_engine_enable_timing",
-    "rt_engine_get_timing", "rt_engine_join",
+    "rt_engine_get_timing", "rt_engine_join", "rt_engine_last_counts",
 )
 
 
@@ -83,6 +83,7 @@ def load_library() -> ctypes.CDLL:
     lib.rt_engine_launch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_size_t]
     lib.rt_engine_fetch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
     lib.rt_engine_join.argtypes = [ctypes.c_void_p]
+    lib.rt_engine_last_counts.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
     lib.rt_engine_shape.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int32)] * 3
     lib.rt_engine_read_spectrogram.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]
     lib.rt_engine_read_row_means.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]
@@ -205,6 +206,12 @@ class Engine:
 
     def set_stream(self, cuda_stream: int) -> None:
         _check(self._lib.rt_engine_set_stream(self._h, ctypes.c_void_p(cuda_stream)))
+
+    def last_counts(self) -> tuple:
+        """(probe hits handed to the extraction kernel, records emitted) of the last fetched launch."""
+        w, r = ctypes.c_int32(0), ctypes.c_int32(0)
+        _check(self._lib.rt_engine_last_counts(self._h, ctypes.byref(w), ctypes.byref(r)))
+        return w.value, r.value
 
     def join(self) -> None:
         """Make the launch stream wait for the scan kernels of every launch so far (they run on an

@@ -38,7 +38,7 @@ void run_k(Ctx& c, kern_t kern, int THREADS, int SMEM, const char* name, int chu
     cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
     SpectroArgs a;
     a.iq = c.d_iq; a.stream_stride = c.stride; a.n = 256; a.T = c.T; a.chunk_segs = chunk;
-    a.n_chunks = (c.T + chunk - 1) / chunk; a.win = c.d_win; a.tw = c.d_tw; a.S = c.d_S; a.part = c.d_part; a.avg = nullptr; a.ctr = nullptr;
+    a.n_chunks = (c.T + chunk - 1) / chunk; a.win = c.d_win; a.tw = c.d_tw; a.S = c.d_S; a.S_stream_stride = (size_t)c.T * 256; a.part = c.d_part;
     if ((size_t)a.n_chunks * c.streams * 256 > c.part_elems) { printf("%s: part buffer too small\n", name); return; }
     CK(cudaMemset(c.d_part, 0, c.part_elems * 4));
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));

@@ -55,7 +55,7 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&d_part7, (size_t)streams * n_chunks * 256 * 4));
     SpectroArgs a7;
     a7.iq = d_iq; a7.stream_stride = stride; a7.n = 256; a7.T = T; a7.chunk_segs = chunk; a7.n_chunks = n_chunks;
-    a7.win = d_win; a7.tw = d_tw; a7.S = d_S7; a7.part = d_part7; a7.avg = nullptr; a7.ctr = nullptr;
+    a7.win = d_win; a7.tw = d_tw; a7.S = d_S7; a7.S_stream_stride = (size_t)T * 256; a7.part = d_part7;
     CK(cudaFuncSetAttribute(spectro_reg256_v7<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, R256v7::SMEM));
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     float best7 = 1e9f;
