@@ -584,6 +584,11 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     e->reg256 = (n == 256) && (cfg->fft_impl != RT_FFT_GENERIC);
     e->tc256 = cfg->fft_impl == RT_FFT_TC256;
     e->chunk_segs = e->reg256 ? 256 : 32;
+    if (e->reg256) {
+        // short blocks (300 kS/s SDRs, replay): shorter chunks = more CTAs per stream.  The choice depends on T only, so a
+        // stream gives bit-identical row means whether it runs alone or inside a batch.
+        e->chunk_segs = e->T >= 4096 ? 256 : (e->T >= 2048 ? 128 : 64);
+    }
     if (const char* cs = std::getenv("RT_CHUNK_SEGS")) { const int v = std::atoi(cs); if (e->reg256 && v >= 8 && v % 8 == 0) e->chunk_segs = v; }
     if (const char* sh = std::getenv("RT_SCAN_SHAPE")) {
         int a = 0, b = 0, c = 0;

@@ -400,7 +400,24 @@ __device__ __forceinline__ void lane_byte_sums(uint32_t addr, unsigned& sI, unsi
     sI = __dp4a(q1.w, 0x00010001u, sI); sQ = __dp4a(q1.w, 0x01000100u, sQ);
 }
 
-template <bool STORE, bool HINT = false, int MINB = 4, bool TWS = false, bool WINS = false>
+// the same sums on the ALU pipe (LOP3 / PRMT field extraction + IADD3) instead of 16 dp4a, which cost two FMA-pipe
+// slots each: the kernel is FMA-pipe bound and its ALU pipe is 20 % busy
+__device__ __forceinline__ void lane_byte_sums_alu(uint32_t addr, unsigned& sI, unsigned& sQ) {
+    const uint4 q0 = lds_128(addr), q1 = lds_128(addr + 256);
+    const unsigned m = 0x00ff00ffu;
+    // 16-bit fields (even sample | odd sample << 16); eight words of <= 255 each stay below 2^16
+    const unsigned aI = (q0.x & m) + (q0.y & m) + (q0.z & m);
+    const unsigned bI = (q0.w & m) + (q1.x & m) + (q1.y & m);
+    const unsigned cI = (q1.z & m) + (q1.w & m);
+    const unsigned aQ = __byte_perm(q0.x, 0, 0x4341) + __byte_perm(q0.y, 0, 0x4341) + __byte_perm(q0.z, 0, 0x4341);
+    const unsigned bQ = __byte_perm(q0.w, 0, 0x4341) + __byte_perm(q1.x, 0, 0x4341) + __byte_perm(q1.y, 0, 0x4341);
+    const unsigned cQ = __byte_perm(q1.z, 0, 0x4341) + __byte_perm(q1.w, 0, 0x4341);
+    const unsigned tI = aI + bI + cI, tQ = aQ + bQ + cQ;
+    sI = (tI & 0xffffu) + (tI >> 16);
+    sQ = (tQ & 0xffffu) + (tQ >> 16);
+}
+
+template <bool STORE, bool HINT = false, int MINB = 4, bool TWS = false, bool WINS = false, bool ALUSUM = false>
 __global__ void __launch_bounds__(R256v7::THREADS, MINB) spectro_reg256_v7(SpectroArgs a) {
     using C = R256v7;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -478,7 +495,8 @@ __global__ void __launch_bounds__(R256v7::THREADS, MINB) spectro_reg256_v7(Spect
     // segment byte sums -> detrend constant (32768 + mean_I, 32768 + mean_Q), exact in fp32
     auto detrend_of = [&](uint32_t addr) {
         unsigned sI, sQ;
-        lane_byte_sums(addr, sI, sQ);
+        if (ALUSUM) lane_byte_sums_alu(addr, sI, sQ);
+        else lane_byte_sums(addr, sI, sQ);
         // warp-wide REDUX: half-warp 0 in the low 16 bits, half-warp 1 in the high 16 (each total < 2^16)
         const unsigned tI = __reduce_add_sync(0xffffffffu, sI << (16 * h));
         const unsigned tQ = __reduce_add_sync(0xffffffffu, sQ << (16 * h));

@@ -159,6 +159,9 @@ int main(int argc, char** argv) {
     run<V6n>(c, "v6 no S store", 256);
     run_k(c, spectro_reg256_v7<true>, R256v7::THREADS, R256v7::SMEM, "v7", 256);
     run_k(c, spectro_reg256_v7<false>, R256v7::THREADS, R256v7::SMEM, "v7 no store", 256);
+    run_k(c, spectro_reg256_v7<true, false, 4, false, false, true>, R256v7::THREADS, R256v7::SMEM, "v7 alu sums", 256);
+    run_k(c, spectro_reg256_v7<false, false, 4, false, false, true>, R256v7::THREADS, R256v7::SMEM, "v7 alu sums no store", 256);
+    run_k(c, spectro_reg256_v7<true, false, 4, false, false, true>, R256v7::THREADS, R256v7::SMEM, "v7 alu sums chunk 128", 128);
     run_k(c, spectro_reg256_v7<true>, R256v7::THREADS, R256v7::SMEM, "v7 chunk 128", 128);
     run_k(c, spectro_reg256_v7<true, false, 5, true, false>, R256v7::THREADS, R256v7::SMEM, "v7 tw-smem minb5", 256);
     run_k(c, spectro_reg256_v7<true, false, 6, true, false>, R256v7::THREADS, R256v7::SMEM, "v7 tw-smem minb6", 256);
