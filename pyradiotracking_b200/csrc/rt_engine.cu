@@ -29,6 +29,7 @@
 #include "../../include/rt_engine.h"
 #include "spectro256.cuh"
 #include "spectro_tc256.cuh"
+#include "spectro_r16.cuh"
 
 namespace {
 
@@ -199,6 +200,13 @@ __device__ __forceinline__ float row_mean_of(const float* part, int s, int fi, i
         for (int i = 0; i < 16; ++i) t[i & 3] += (double)v[i];
     }
     return (float)(((t[0] + t[1]) + (t[2] + t[3])) / (double)T);
+}
+
+// stand-alone row means for kernels that leave many partial rows per stream (spectro_r16: one per CTA): the probe
+// kernel's prologue would repeat the long reduction in every probe group
+__global__ void row_mean_kernel(const float* part, float* avg, int n, int n_chunks, int T) {
+    const int fi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fi < n) avg[blockIdx.y * n + fi] = row_mean_of(part, blockIdx.y, fi, n, n_chunks, T);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -446,12 +454,13 @@ struct rt_engine {
     int n = 0, T = 0, n_streams = 0, n_chunks = 0, chunk_segs = 0, n_probes = 0;
     bool reg256 = false;                     // nperseg 256: register kernel (v7) or tensor-core kernel; TILE layout
     bool tc256 = false;                      // tensor-core stage 1 (spectro_tc256.cuh)
+    bool r16 = false;                        // nperseg 1024 / 4096: radix-16 Stockham kernel (spectro_r16.cuh), LINEAR layout
     size_t s_stride = 0;                     // floats per stream in a spectrogram buffer
     float pscale = 1.f;                      // power factor carried by S / row means / thresholds (tensor-core path), a power of two
     uint4* d_bmat = nullptr;                 // tensor-core operand image
     rt::TcTables tc_tab;
     int tc_grid = 0, tc_slots = 1, tc_bps = 0;
-    int probe_threads = 256, extract_threads = 256, extract_ctas = 148 * 8;   // scan launch shapes (RT_SCAN_SHAPE=probe,extract,ctas)
+    int probe_threads = 256, extract_threads = 128, extract_ctas = 148 * 16;   // scan launch shapes (RT_SCAN_SHAPE=probe,extract,ctas)
     float* d_win = nullptr;
     float2* d_tw = nullptr;
     // three spectrogram buffers: launch i writes S[i % 3] while the scan of launch i-1 still reads
@@ -583,6 +592,7 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     if (cfg->fft_impl < RT_FFT_AUTO || cfg->fft_impl > RT_FFT_TC256) { delete e; return fail(RT_ERR_INVALID, "unknown fft_impl"); }
     e->reg256 = (n == 256) && (cfg->fft_impl != RT_FFT_GENERIC);
     e->tc256 = cfg->fft_impl == RT_FFT_TC256;
+    e->r16 = (n == 1024 || n == 4096) && cfg->fft_impl == RT_FFT_AUTO;
     e->chunk_segs = e->reg256 ? 256 : 32;
     if (e->reg256) {
         // short blocks (300 kS/s SDRs, replay): shorter chunks = more CTAs per stream.  The choice depends on T only, so a
@@ -595,6 +605,12 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
         if (std::sscanf(sh, "%d,%d,%d", &a, &b, &c) == 3 && a >= 32 && a <= 1024 && a % 32 == 0 && b >= 32 && b <= 1024 && b % 32 == 0 && c >= 1) { e->probe_threads = a; e->extract_threads = b; e->extract_ctas = c; }
     }
     e->n_chunks = (e->T + e->chunk_segs - 1) / e->chunk_segs;
+    if (e->r16) {
+        // segments are dealt round-robin over n_chunks CTAs (x teams) per stream; 296 = 148 SMs x 2 resident CTAs
+        const int teams = n == 4096 ? 1 : 4;
+        e->n_chunks = std::min(296, (e->T + teams - 1) / teams);
+        e->chunk_segs = (e->T + e->n_chunks - 1) / e->n_chunks;      // informational
+    }
     e->s_stride = e->tc256 ? (size_t)((e->T + 31) / 32) * 8192 : (size_t)e->T * n;
 
 #define CUE(call)                                                                                  \
@@ -682,6 +698,10 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     CUE(cudaMemcpy(e->d_thr, hthr.data(), e->n_streams * sizeof(float), cudaMemcpyHostToDevice));
     e->h_hasprev.assign(e->n_streams, 0);
     e->hasprev_dirty = true;
+    if (e->r16) {
+        if (n == 4096) CUE(cudaFuncSetAttribute(rt::spectro_r16_k<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R16Cfg<4096>::SMEM));
+        else CUE(cudaFuncSetAttribute(rt::spectro_r16_k<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R16Cfg<1024>::SMEM));
+    }
     if (!e->reg256) {
         const size_t smem = (size_t)n * (2 * sizeof(float2) + sizeof(float)) + 16;
         CUE(cudaFuncSetAttribute(spectro_generic<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -796,6 +816,9 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
         rt::spectro_tc256_k<2><<<e->tc_grid, 512, rt::Tc256<2>::SMEM, st>>>(ta);
     } else if (use_reg) {
         rt::spectro_reg256_v7<true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
+    } else if (e->r16 && aligned) {
+        if (e->n == 4096) rt::spectro_r16_k<4096><<<grid, 256, rt::R16Cfg<4096>::SMEM, st>>>(sa);
+        else rt::spectro_r16_k<1024><<<grid, 256, rt::R16Cfg<1024>::SMEM, st>>>(sa);
     } else {
         const size_t smem = (size_t)e->n * (2 * sizeof(float2) + sizeof(float)) + 16;
         spectro_generic<256><<<grid, 256, smem, st>>>(sa);
@@ -813,10 +836,15 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     }
     CU(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), sc_st));
     if (evs) CU(cudaEventRecord(evs->ev[2], sc_st));
+    const bool sep_mean = !(use_reg && e->tc256) && e->n_chunks > 64;
+    if (sep_mean) {
+        row_mean_kernel<<<dim3((e->n + 127) / 128, e->n_streams), 128, 0, sc_st>>>(e->d_part[slot], e->d_avg[slot], e->n, e->n_chunks, e->T);
+        CU(cudaGetLastError());
+    }
     if (evs) CU(cudaEventRecord(evs->ev[3], sc_st));
 
     ScanArgs sc;
-    sc.S = e->d_S[next]; sc.Sprev = e->d_S[e->cur]; sc.stream_stride = e->s_stride; sc.avg = e->d_avg[slot]; sc.part = (use_reg && e->tc256) ? nullptr : e->d_part[slot]; sc.n_chunks = e->n_chunks; sc.thr = e->d_thr; sc.has_prev = e->d_hasprev;
+    sc.S = e->d_S[next]; sc.Sprev = e->d_S[e->cur]; sc.stream_stride = e->s_stride; sc.avg = e->d_avg[slot]; sc.part = ((use_reg && e->tc256) || sep_mean) ? nullptr : e->d_part[slot]; sc.n_chunks = e->n_chunks; sc.thr = e->d_thr; sc.has_prev = e->d_hasprev;
     sc.snr = (float)e->cfg.snr_threshold;
     sc.n = e->n; sc.T = e->T; sc.stride = e->cfg.probe_stride; sc.n_probes = e->n_probes;
     sc.min_cols = e->cfg.min_cols; sc.max_cols = e->cfg.max_cols;
@@ -842,7 +870,7 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
         if (!h) { h = 1; e->hasprev_dirty = true; }
     e->launched = true;
     e->acc.launches += 1;
-    e->acc.kernels += 3;
+    e->acc.kernels += sep_mean ? 4 : 3;
     return RT_OK;
 }
 

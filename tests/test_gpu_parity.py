@@ -16,6 +16,8 @@ pytestmark = pytest.mark.gpu
 
 
 def _impls(nperseg, window="hamming"):
+    if nperseg in (1024, 4096):
+        return [E.FFT_GENERIC, E.FFT_AUTO]           # AUTO = radix-16 Stockham kernel (spectro_r16.cuh)
     if nperseg != 256:
         return [E.FFT_GENERIC]
     impls = [E.FFT_GENERIC, E.FFT_REG256]
