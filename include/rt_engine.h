@@ -151,6 +151,15 @@ int rt_engine_shape(const rt_engine *e, int32_t *n_streams, int32_t *nperseg, in
 int rt_engine_read_spectrogram(rt_engine *e, int32_t stream, float *out_T_by_nperseg);
 int rt_engine_read_row_means(rt_engine *e, int32_t stream, float *out_nperseg);
 
+/*
+ * Parity hook (tests only, no GPU needed): the constant operands of the RT_FFT_TC256 kernel for a 256-point window
+ * (as scipy returns it): the 16 stage-1 matrices as two fp16 terms in the tensor-core operand layout
+ * (bmat_out: 16 * 2 * 1024 halves, element (n, k) of matrix (n2, hi|lo) at ((n2*2 + hl)*1024 + (n>>3)*256 + (k>>3)*64 + (n&7)*8 + (k&7)),
+ * n = 2*k1 + re|im, k = 2*n1 + I|Q), the scaled window DFT at the bins 0, 1, 255 (wc_out: 3 complex), the power-of-two
+ * power scale, and whether the window qualifies (its DFT vanishes outside the bins 0 and +-1).
+ */
+int rt_tc256_tables(const double *window, double sample_rate, uint16_t *bmat_out, double *wc_out, double *pscale_out, int32_t *eligible_out);
+
 /* CUDA-event timing of the individual kernels (bench.py roofline). */
 int rt_engine_enable_timing(rt_engine *e, int32_t on);
 int rt_engine_get_timing(rt_engine *e, rt_timing *out, int32_t reset);

@@ -911,6 +911,19 @@ int rt_engine_fetch(rt_engine* e, rt_record* out, int32_t max_out, int32_t* n_ou
     return RT_OK;
 }
 
+int rt_tc256_tables(const double* window, double sample_rate, uint16_t* bmat_out, double* wc_out, double* pscale_out, int32_t* eligible_out) {
+    if (!window || !(sample_rate > 0)) return fail(RT_ERR_INVALID, "null window / bad sample rate");
+    double sw2 = 0.0;
+    for (int i = 0; i < 256; ++i) sw2 += window[i] * window[i];
+    if (!(sw2 > 0)) return fail(RT_ERR_INVALID, "window has no energy");
+    const rt::TcTables t = rt::tc_make_tables(window, std::sqrt(1.0 / (sample_rate * sw2)) / 127.5);
+    if (bmat_out) std::memcpy(bmat_out, t.bmat.data(), t.bmat.size() * sizeof(uint16_t));
+    if (wc_out) { wc_out[0] = t.wc0.x; wc_out[1] = t.wc0.y; wc_out[2] = t.wc1.x; wc_out[3] = t.wc1.y; wc_out[4] = t.wc255.x; wc_out[5] = t.wc255.y; }
+    if (pscale_out) *pscale_out = (double)t.pscale;
+    if (eligible_out) *eligible_out = t.eligible ? 1 : 0;
+    return RT_OK;
+}
+
 int rt_engine_last_counts(rt_engine* e, int32_t* work_items, int32_t* records) {
     if (!e) return fail(RT_ERR_INVALID, "null engine");
     if (work_items) *work_items = e->last_work_items;

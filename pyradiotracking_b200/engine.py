@@ -21,7 +21,7 @@ EXPORTS = (
     "rt_last_error", "rt_abi_version", "rt_device_count", "rt_engine_create", "rt_engine_destroy",
     "rt_engine_set_stream", "rt_engine_reset_stream", "rt_engine_process", "rt_engine_launch", "rt_engine_fetch",
     "rt_engine_shape", "rt_engine_read_spectrogram", "rt_engine_read_row_means", "rt_engine_enable_timing",
-    "rt_engine_get_timing", "rt_engine_join", "rt_engine_last_counts",
+    "rt_engine_get_timing", "rt_engine_join", "rt_engine_last_counts", "rt_tc256_tables",
 )
 
 
@@ -83,6 +83,7 @@ def load_library() -> ctypes.CDLL:
     lib.rt_engine_launch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_size_t]
     lib.rt_engine_fetch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
     lib.rt_engine_join.argtypes = [ctypes.c_void_p]
+    lib.rt_tc256_tables.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.rt_engine_last_counts.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
     lib.rt_engine_shape.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int32)] * 3
     lib.rt_engine_read_spectrogram.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]
@@ -237,3 +238,19 @@ class Engine:
         t = RtTiming()
         _check(self._lib.rt_engine_get_timing(self._h, ctypes.byref(t), int(reset)))
         return {k: getattr(t, k) for k, _ in RtTiming._fields_}
+
+
+def tc256_tables(window, sample_rate: float):
+    """Constant operands of the tensor-core spectrogram kernel (parity hook, CPU only): (bmat uint16 [16, 2, 1024] in the
+    operand layout, wc complex128 [3] for the bins 0 / 1 / 255, pscale, eligible)."""
+    lib = load_library()
+    w = np.ascontiguousarray(window, dtype=np.float64)
+    if w.shape != (256,):
+        raise ValueError("the tensor-core kernel is a 256-point kernel")
+    bmat = np.zeros((16, 2, 1024), dtype=np.uint16)
+    wc = np.zeros(6, dtype=np.float64)
+    ps = ctypes.c_double(0.0)
+    el = ctypes.c_int32(0)
+    _check(lib.rt_tc256_tables(w.ctypes.data_as(ctypes.c_void_p), float(sample_rate), bmat.ctypes.data_as(ctypes.c_void_p),
+                               wc.ctypes.data_as(ctypes.c_void_p), ctypes.byref(ps), ctypes.byref(el)))
+    return bmat, wc.view(np.complex128), ps.value, bool(el.value)

@@ -23,7 +23,7 @@ def test_library_builds_loads_and_exports_header_symbols():
     B.build()
     lib = E.load_library()
     hdr = open(os.path.join(ROOT, "include", "rt_engine.h")).read()
-    declared = set(re.findall(r"\b(rt_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(rt_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(E.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
@@ -146,3 +146,90 @@ def test_timedelta_us_matches_cpython_rounding():
                         np.arange(-3000, 3000) * 0.0000005])
     want = [(lambda td: (td.days * 86400 + td.seconds) * 1000000 + td.microseconds)(datetime.timedelta(seconds=float(v))) for v in x]
     assert timedelta_us(x).tolist() == want
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tensor-core spectrogram path (csrc/spectro_tc256.cuh): the shipped operand tables + the kernel's algebra on the CPU
+# ---------------------------------------------------------------------------------------------------------
+def _tc_matrices(bmat):
+    """[16 n2, 2 hi|lo, 32 n, 32 k] float64 from the operand image (core-matrix layout of the header comment)."""
+    n, k = np.meshgrid(np.arange(32), np.arange(32), indexing="ij")
+    off = (n >> 3) * 256 + (k >> 3) * 64 + (n & 7) * 8 + (k & 7)
+    return bmat.view(np.float16)[:, :, off].astype(np.float64)
+
+
+@pytest.mark.parametrize("window", ["hamming", "hann", "boxcar"])
+def test_tensor_core_tables_and_stage_algebra_on_cpu(window):
+    fs = 2_400_000
+    w = R.resolve_window(window, 256)
+    bmat, wc, pscale, eligible = E.tc256_tables(w, fs)
+    assert eligible and pscale > 0 and np.log2(pscale) == int(np.log2(pscale))
+    B = _tc_matrices(bmat)                                   # hi and lo terms
+    amp = np.sqrt(1.0 / (fs * np.sum(w * w))) / 127.5
+    sc = np.sqrt(pscale)
+    # (1) hi + lo reproduces  w'[n] e^{-2 pi j k1 n / 256}  to ~2^-22: D[(k1,re)] = sum xI cr - xQ ci, D[(k1,im)] = sum xI ci + xQ cr
+    for n2 in (0, 5, 15):
+        nn = 16 * np.arange(16) + n2
+        c = (w[nn] * amp * sc)[None, :] * np.exp(-2j * np.pi * np.outer(np.arange(16), nn) / 256.0)     # [k1, n1]
+        want = np.empty((32, 32))
+        want[0::2, 0::2], want[0::2, 1::2] = c.real, -c.imag
+        want[1::2, 0::2], want[1::2, 1::2] = c.imag, c.real
+        got = B[n2, 0] + B[n2, 1]
+        assert np.max(np.abs(got - want)) <= 2.0 ** -21 * np.max(np.abs(want))
+        assert np.max(np.abs(B[n2, 1])) <= 2.0 ** -11 * np.max(np.abs(B[n2, 0]))
+    # (2) the kernel's algebra in float32 accumulation: stage 1 (exact bytes x split matrix), DFT16 over n2, 3-bin detrend
+    cap = synth.make_stream(synth.C2, 3, 1)[0][: 512 * 40].reshape(40, 256, 2).astype(np.int64)
+    cap[7] += 9                                              # a segment with a DC offset
+    cap = np.clip(cap, 0, 255)
+    x = (cap - 128).astype(np.float32)                       # exact in fp16
+    A = x.reshape(40, 16, 16, 2).transpose(0, 2, 1, 3).reshape(40, 16, 32)      # [seg, n2, (n1, iq)]
+    U = np.zeros((40, 16, 32), np.float32)
+    for hl in (0, 1):
+        U += np.einsum("snk,nmk->snm", A, B[:, hl].astype(np.float32), dtype=np.float32)
+    Uc = (U[:, :, 0::2] + 1j * U[:, :, 1::2]).astype(np.complex64)              # [seg, n2, k1]
+    X = np.fft.fft(Uc, axis=1)                                                  # over n2 -> k2: bin = k1 + 16 k2
+    Xk = np.empty((40, 256), np.complex128)
+    for k1 in range(16):
+        Xk[:, k1 + 16 * np.arange(16)] = X[:, :, k1]
+    m = (cap.sum(axis=1) - 32768) / 256.0                                        # residual mean, exact
+    mres = m[:, 0] + 1j * m[:, 1]
+    for k, c in zip((0, 1, 255), wc):
+        Xk[:, k] -= mres * c
+    got = (np.abs(Xk) ** 2) / pscale
+    iq = synth.bytes_to_iq(cap.astype(np.uint8).reshape(-1))
+    _, _, S = R.spectrogram(iq, fs, window, 256)
+    ref = S.T
+    big = ref >= 1e-4 * ref.max(axis=1, keepdims=True)      # within 40 dB of the column maximum: fp32 accumulation floor
+    assert np.max(np.abs(got[big] - ref[big]) / ref[big]) < 5e-5
+    # windows whose DFT leaks beyond the bins 0, +-1 are refused
+    assert not E.tc256_tables(R.resolve_window(("kaiser", 8.0), 256), fs)[3]
+    assert not E.tc256_tables(R.resolve_window("blackman", 256), fs)[3]
+
+
+@pytest.mark.parametrize("N", [1024, 4096])
+def test_radix16_stockham_index_algebra_on_cpu(N):
+    """The pass structure of csrc/spectro_r16.cuh (read/write indices, twiddles, last pass in registers) vs numpy."""
+    rng = np.random.default_rng(N)
+    x = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    tw = np.exp(-2j * np.pi * np.arange(N) / N)
+    i16 = np.arange(16)
+    F16 = np.exp(-2j * np.pi * np.outer(i16, i16) / 16)
+    BT, M1, M2 = N // 16, N // 16, N // 256
+    X = np.zeros(N, complex)
+    for b in range(BT):                                      # pass 1: inputs b + M1 i -> y[16 b + i] * W_N^{b i}
+        v = F16 @ x[b + M1 * i16]
+        X[16 * b + i16] = v * tw[(b * i16) % N]
+    Y = np.zeros(N, complex)
+    for b in range(BT):                                      # pass 2: p = b / 16, q = b % 16
+        p, q = b >> 4, b & 15
+        v = F16 @ X[q + 16 * (p + M2 * i16)]
+        Y[q + 16 * (16 * p + i16)] = v * tw[(16 * p * i16) % N]
+    out = np.zeros(N, complex)
+    if N == 4096:
+        for b in range(256):
+            out[b + 256 * i16] = F16 @ Y[b + 256 * i16]
+    else:
+        F4 = np.exp(-2j * np.pi * np.outer(np.arange(4), np.arange(4)) / 4)
+        for q in range(256):
+            out[q + 256 * np.arange(4)] = F4 @ Y[q + 256 * np.arange(4)]
+    assert np.max(np.abs(out - np.fft.fft(x))) < 1e-9 * N
