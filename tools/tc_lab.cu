@@ -74,12 +74,15 @@ int main(int argc, char** argv) {
     int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
     TcArgs at;
     at.iq = d_iq; at.stream_stride = stride; at.T = T; at.n_streams = streams;
-    const int rows = 128 / NGsel;
+    const bool wspec = NGsel == 3;                  // 3: pipelined kernel spectro_tcp256_k
+    const int NGv = NGsel == 2 ? 2 : 1;
+    const int rows = 128 / NGv;
     at.bps = (T + rows - 1) / rows; at.total_batches = streams * at.bps;
-    const int G = std::max(1, std::min(sms, at.total_batches / NGsel));
-    const long long GV = (long long)NGsel * G;
-    void (*kern)(TcArgs) = NGsel == 2 ? spectro_tc256_k<2> : spectro_tc256_k<1>;
-    const int SMEM = NGsel == 2 ? Tc256<2>::SMEM : Tc256<1>::SMEM;
+    const int G = std::max(1, std::min(sms, at.total_batches / NGv));
+    const long long GV = (long long)NGv * G;
+    void (*kern)(TcArgs) = wspec ? spectro_tcp256_k : (NGsel == 2 ? spectro_tc256_k<2> : spectro_tc256_k<1>);
+    const int SMEM = wspec ? Tcp256::SMEM : (NGsel == 2 ? Tc256<2>::SMEM : Tc256<1>::SMEM);
+    const int NTHR = 512;
     int slots = 1;
     for (int s = 0; s < streams; ++s) {
         slots = std::max(slots, tc_last_run(s, at.bps, GV, at.total_batches) - tc_first_run(s, at.bps, GV, at.total_batches) + 1);
@@ -104,7 +107,7 @@ int main(int argc, char** argv) {
     float bestt = 1e9f, tot = 0;
     for (int i = 0; i < 3 + reps; ++i) {
         CK(cudaEventRecord(e0));
-        kern<<<G, 512, SMEM>>>(at);
+        kern<<<G, NTHR, SMEM>>>(at);
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (i >= 3) { bestt = std::min(bestt, ms); tot += ms; }
         if (i == 0) { CK(cudaGetLastError()); CK(cudaDeviceSynchronize()); printf("first launch ok: %.2f us\n", ms * 1e3); fflush(stdout); }
@@ -116,28 +119,50 @@ int main(int argc, char** argv) {
     float bestn = 1e9f;
     for (int i = 0; i < reps; ++i) {
         CK(cudaEventRecord(e0));
-        kern<<<G, 512, SMEM>>>(at);
+        kern<<<G, NTHR, SMEM>>>(at);
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); bestn = std::min(bestn, ms);
     }
     printf("tc kernel, no S store: best %.2f us\n", 1e3 * bestn);
 
-    {
-        unsigned long long* d_prof; CK(cudaMalloc(&d_prof, G * 32 * NGsel));
+    if (!wspec) {
+        unsigned long long* d_prof; CK(cudaMalloc(&d_prof, G * 32 * NGv));
         at.prof = d_prof;
         for (int st = 1; st >= 0; --st) {
             at.store = st; at.dbg = 0;
-            kern<<<G, 512, SMEM>>>(at);
+            kern<<<G, NTHR, SMEM>>>(at);
             CK(cudaDeviceSynchronize());
-            std::vector<unsigned long long> hp(G * 4 * NGsel);
-            CK(cudaMemcpy(hp.data(), d_prof, G * 32 * NGsel, cudaMemcpyDeviceToHost));
+            std::vector<unsigned long long> hp(G * 4 * NGv);
+            CK(cudaMemcpy(hp.data(), d_prof, G * 32 * NGv, cudaMemcpyDeviceToHost));
             double ph[4] = {0, 0, 0, 0};
-            for (int i = 0; i < G * 4 * NGsel; ++i) ph[i & 3] += (double)hp[i] / (NGsel * G);
-            const double nb = (double)at.total_batches / (NGsel * G);
+            for (int i = 0; i < G * 4 * NGv; ++i) ph[i & 3] += (double)hp[i] / (NGv * G);
+            const double nb = (double)at.total_batches / (NGv * G);
             printf("phase cycles per half-batch per warp group (store %d dbg %d): convert %.0f  mma-wait %.0f  consume %.0f  flush(per run) %.0f   [half-batches per run %.1f]\n", at.store, at.dbg, ph[0] / nb, ph[1] / nb, ph[2] / nb, ph[3], nb);
         }
         at.prof = nullptr; at.store = 1; at.dbg = 0;
-        kern<<<G, 512, SMEM>>>(at);
+        kern<<<G, NTHR, SMEM>>>(at);
+        CK(cudaDeviceSynchronize());
+    }
+    if (wspec) {
+        const size_t pbytes = (size_t)G * 16 * 4 * 8;
+        unsigned long long* d_prof; CK(cudaMalloc(&d_prof, pbytes));
+        at.prof = d_prof;
+        for (int var = 0; var < 2; ++var) {
+            const int st = var == 0 ? 1 : 0;
+            at.store = st; at.dbg = 0;
+            CK(cudaMemset(d_prof, 0, pbytes));
+            kern<<<G, NTHR, SMEM>>>(at);
+            CK(cudaDeviceSynchronize());
+            std::vector<unsigned long long> hp((size_t)G * 64);
+            CK(cudaMemcpy(hp.data(), d_prof, pbytes, cudaMemcpyDeviceToHost));
+            const double nb = (double)at.total_batches / G;
+            double ph[4] = {0, 0, 0, 0}, w0[4] = {0, 0, 0, 0};
+            for (size_t i = 0; i < hp.size(); ++i) { ph[i & 3] += (double)hp[i] / (G * 16.0); if (((i >> 2) & 15) == 0) w0[i & 3] += (double)hp[i] / G; }
+            printf("cycles per batch per warp (store %d): convert %.0f  wait d_full %.0f  consume %.0f  flush (per run) %.0f | warp 0 (MMA issuer): convert %.0f  wait %.0f  consume %.0f   [batches per CTA %.1f]\n",
+                   st, ph[0] / nb, ph[1] / nb, ph[2] / nb, ph[3], w0[0] / nb, w0[1] / nb, w0[2] / nb, nb);
+        }
+        at.prof = nullptr; at.store = 1; at.dbg = 0;
+        kern<<<G, NTHR, SMEM>>>(at);
         CK(cudaDeviceSynchronize());
     }
     // ---------------- compare
