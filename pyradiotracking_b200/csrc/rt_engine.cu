@@ -446,6 +446,9 @@ __global__ void untile_kernel(const float* S, float* out, int total, float inv_s
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// error text for the other translation units of the library (rt_matcher.cpp)
+int rt_internal_fail(int code, const char* msg) { return fail(code, msg); }
+
 struct rt_engine {
     rt_config cfg{};
     int dev = 0;
@@ -765,8 +768,11 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
         }
         const int sb = (int)(e->h2d_seq & 1);
         if (e->h2d_seq >= 2) CU(cudaStreamWaitEvent(e->h2d_stream, e->stage_free[sb], 0));   // the spectrogram kernel that read this buffer is done
-        CU(cudaMemcpy2DAsync(e->d_stage[sb], e->stage_stride, iq, stream_stride_bytes, block_bytes, e->n_streams,
-                             cudaMemcpyHostToDevice, e->h2d_stream));
+        if (e->stage_stride == stream_stride_bytes || e->n_streams == 1)    // packed batch: one linear DMA instead of n_streams row copies
+            CU(cudaMemcpyAsync(e->d_stage[sb], iq, e->n_streams == 1 ? block_bytes : e->stage_stride * e->n_streams, cudaMemcpyHostToDevice, e->h2d_stream));
+        else
+            CU(cudaMemcpy2DAsync(e->d_stage[sb], e->stage_stride, iq, stream_stride_bytes, block_bytes, e->n_streams,
+                                 cudaMemcpyHostToDevice, e->h2d_stream));
         CU(cudaEventRecord(e->h2d_done[sb], e->h2d_stream));
         CU(cudaStreamWaitEvent(st, e->h2d_done[sb], 0));
         d_iq = e->d_stage[sb];

@@ -22,6 +22,9 @@ EXPORTS = (
     "rt_engine_set_stream", "rt_engine_reset_stream", "rt_engine_process", "rt_engine_launch", "rt_engine_fetch",
     "rt_engine_shape", "rt_engine_read_spectrogram", "rt_engine_read_row_means", "rt_engine_enable_timing",
     "rt_engine_get_timing", "rt_engine_join", "rt_engine_last_counts", "rt_tc256_tables",
+    # include/rt_matcher.h
+    "rt_matcher_create", "rt_matcher_destroy", "rt_matcher_add", "rt_matcher_pending", "rt_matcher_drain",
+    "rt_matcher_open", "rt_matcher_read_open",
 )
 
 

@@ -108,3 +108,56 @@ def message_types() -> Tuple[type, type]:
 
 def _isfinite(x: float) -> bool:
     return not (math.isnan(x) or math.isinf(x))
+
+
+class MatchingSignal(_Message):
+    """A group of Signals of different devices that belong to one transmission
+    (reference: radiotracking/__init__.py:205-334, MatchedSignal + MatchingSignal).
+
+    `_sigs` maps device name -> Signal in first-insertion order; ts / duration / frequency / `_avgs` are the
+    reference's derived views (earliest start, longest duration, median frequency, per-device average power).
+    """
+
+    def __init__(self, devices: List[str]):
+        self.devices = devices
+        self._sigs: Dict[str, Signal] = {}
+
+    @property
+    def duration(self) -> datetime.timedelta:
+        return max(sig.duration for sig in self._sigs.values())
+
+    @property
+    def ts(self) -> datetime.datetime:
+        return min(sig.ts for sig in self._sigs.values())
+
+    @property
+    def frequency(self) -> float:
+        import statistics
+
+        return statistics.median(sig.frequency for sig in self._sigs.values())
+
+    @property
+    def _avgs(self) -> List[Any]:
+        return [self._sigs[d].avg if d in self._sigs else None for d in self.devices]
+
+    @property
+    def header(self) -> List[str]:  # type: ignore[override]
+        return ["Time", "Frequency", "Duration", *self.devices]
+
+    @property
+    def as_list(self) -> List[Any]:
+        return [self.ts, self.frequency, self.duration, *self._avgs]
+
+    def __repr__(self) -> str:
+        return f"MatchedSignal({self.devices}, {self.ts}, {self.frequency}, {self.duration}, " + ", ".join(repr(a) for a in self._avgs) + ")"
+
+
+def matching_signal_type() -> type:
+    """The reference's own MatchingSignal when `radiotracking` is importable (so that `isinstance` checks in
+    consume.py keep working), otherwise the mirror."""
+    try:
+        import radiotracking  # type: ignore
+
+        return radiotracking.MatchingSignal
+    except Exception:
+        return MatchingSignal

@@ -205,3 +205,45 @@ def test_two_blocks_in_flight_equal_sequential_calls():
     finally:
         a.close()
         b.close()
+
+
+def test_batched_signals_through_the_native_matcher_equal_the_oracle_matcher():
+    """SURVEY 8f rank 1 behind the engine: four 'antennas' (streams) hear the same capture with different
+    calibration, two more hear another one; the Signals of every block go through SignalMatcher.add_batch in the
+    queue order of the batch and must group exactly like the restated reference matcher (oracle/matcher.py)."""
+    from oracle import matcher as OM
+    from pyradiotracking_b200.match import SignalMatcher
+
+    w = synth.C1
+    nb = 3
+    a, b = synth.make_stream(w, 0, nb), synth.make_stream(w, 1, nb)
+    cap = np.stack([a, a, a, a, b, b], axis=1)                       # [nb, 6, 2N]
+    cal = [0.0, 0.5, -0.5, 1.0, 0.0, 0.25]
+    devs = [str(i) for i in range(6)]
+    kw = BY_NAME["c1_default_300k"].analyzer_kwargs()
+    ba = BatchAnalyzer(**parity.batch_kwargs(kw, devices=devs, calibration=cal))
+    mk = dict(device=devs, matching_timeout_s=0.5, matching_time_diff_s=0.001, matching_bandwidth_hz=2500.0, matching_duration_diff_ms=2.0)
+    q = _Q()
+    nat = SignalMatcher(signal_queue=q, **mk)
+    ora = OM.OracleMatcher(**mk)
+    t0 = datetime.datetime(2026, 4, 4, 4, 4, 4, tzinfo=datetime.timezone.utc)
+    try:
+        n_sig = 0
+        for blk in range(nb):
+            ts0 = [parity.block_ts(t0, blk, w.block_samples, w.sample_rate)] * 6
+            res = ba.process_blocks(cap[blk], ts0)
+            sigs = [s for per in res for s in per[0]]                # queue order: device by device
+            for k, s in enumerate(sigs):
+                s.idx = n_sig + k
+            n_sig += len(sigs)
+            nat.add_batch(sigs)
+            for s in sigs:
+                ora.add(s)
+        assert n_sig > 0
+        assert OM.groups_as_ids(q.items) == OM.groups_as_ids(ora.emitted)
+        assert OM.groups_as_ids(nat._matched) == OM.groups_as_ids(ora._matched)
+        sizes = [len(g._sigs) for g in q.items + nat._matched]
+        assert max(sizes) >= 4                                       # the four antennas of capture `a` were grouped
+    finally:
+        ba.close()
+        nat.close()

@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_builds_loads_and_exports_header_symbols():
     B.build()
     lib = E.load_library()
-    hdr = open(os.path.join(ROOT, "include", "rt_engine.h")).read()
+    hdr = open(os.path.join(ROOT, "include", "rt_engine.h")).read() + open(os.path.join(ROOT, "include", "rt_matcher.h")).read()
     declared = set(re.findall(r"\b(rt_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(E.EXPORTS)
     for name in declared:
