@@ -204,9 +204,11 @@ __device__ __forceinline__ float row_mean_of(const float* part, int s, int fi, i
 
 // stand-alone row means for kernels that leave many partial rows per stream (spectro_r16: one per CTA): the probe
 // kernel's prologue would repeat the long reduction in every probe group
-__global__ void row_mean_kernel(const float* part, float* avg, int n, int n_chunks, int T) {
+__global__ void row_mean_kernel(const float* part, float* avg, int n, int n_chunks, int T, int part_perm) {
     const int fi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (fi < n) avg[blockIdx.y * n + fi] = row_mean_of(part, blockIdx.y, fi, n, n_chunks, T);
+    // part_perm: the register kernel writes its chunk sums in PERM position order (n == 256)
+    const int src = part_perm ? (((fi >> 6) << 6) | ((fi & 15) << 2) | ((fi >> 4) & 3)) : fi;
+    if (fi < n) avg[blockIdx.y * n + fi] = row_mean_of(part, blockIdx.y, src, n, n_chunks, T);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -218,6 +220,7 @@ struct ScanArgs {
     size_t stream_stride;  // floats per stream
     float* avg;            // [stream][n] row means: written by the probe kernel (from `part`) or by the tensor-core kernel
     const float* part;     // [stream][n_chunks][n] chunk row sums (nullptr: avg is already there)
+    int part_perm;         // the chunk sums are stored in PERM position order (register kernel)
     int n_chunks;
     const float* thr;      // [stream]
     const int* has_prev;   // [stream]
@@ -232,21 +235,27 @@ struct ScanArgs {
 constexpr int PROBE_QUICK = 3;   // cells examined on each side before handing a probe hit to a warp
 constexpr int EX_W = 4;          // 32-cell windows an extraction warp examines per memory round trip
 
-constexpr int PROBE_PPT = 8;     // probe columns per thread (their loads are in flight together)
+constexpr int PROBE_PPT = 32;    // probe columns per thread: their loads are in flight together, and the row-mean prologue
+                                 // is repeated once per PROBE_PPT columns (8 -> 32: 5x fewer instructions, 29 -> see DESIGN 5.4)
 
-// One thread per (stream, bin, group of PROBE_PPT probe columns); blockDim.x bins of one stream per CTA.
+// One thread per (stream, bin, group of PPT probe columns); blockDim.x bins of one stream per CTA.
 // Prologue: the bin's row mean from the chunk sums (analyze.py:374-375) -- every CTA of the stream computes the
 // same value, the CTAs of probe group 0 publish it for the extraction kernel and the parity hook.
-template <int TILE>
+template <int TILE, int PPT>
 __global__ void probe_kernel(ScanArgs a) {
+    static_assert(PPT >= 1 && PPT <= 32, "hit mask is one word");
     const int nbb = (a.n + blockDim.x - 1) / blockDim.x;           // bin blocks
     const int bb = blockIdx.x % nbb, g = blockIdx.x / nbb;
-    const int fi = bb * blockDim.x + threadIdx.x;
+    const int idx = bb * blockDim.x + threadIdx.x;
     const int s = blockIdx.y;
-    if (fi >= a.n) return;
+    if (idx >= a.n) return;
+    // PERM layout: the thread index is the position inside the S row (and inside the chunk-sum rows, which the register
+    // kernel writes in the same order), so a warp reads 128 contiguous bytes per load instead of 2 floats out of each of
+    // 8 sectors; position 64 a + 4 k1 + b holds bin k1 + 16 (4 a + b)
+    const int fi = TILE == LAYOUT_PERM ? ((idx >> 2) & 15) + 16 * (4 * (idx >> 6) + (idx & 3)) : idx;
     float avg;
     if (a.part != nullptr) {
-        avg = row_mean_of(a.part, s, fi, a.n, a.n_chunks, a.T);
+        avg = row_mean_of(a.part, s, a.part_perm ? idx : fi, a.n, a.n_chunks, a.T);
         if (g == 0) a.avg[s * a.n + fi] = avg;
     } else {
         avg = a.avg[s * a.n + fi];
@@ -254,17 +263,19 @@ __global__ void probe_kernel(ScanArgs a) {
     const CellRef col = CellRef::make<TILE>(a.S, a.stream_stride, s, fi, a.n);
     const float thr = a.thr[s], snr = a.snr;
     // ~96 % of the probe cells fail the predicate: only a hit pays for its neighbours
-    float c0[PROBE_PPT];
+    float c0[PPT];
 #pragma unroll
-    for (int i = 0; i < PROBE_PPT; ++i) {
-        const int k = g * PROBE_PPT + i;
-        c0[i] = (k < a.n_probes) ? col.at<TILE>(k * a.stride) : 0.f;
+    for (int i = 0; i < PPT; ++i) {
+        const int k = g * PPT + i;
+        c0[i] = (k < a.n_probes) ? col.at<TILE>(k * a.stride) : -1.f;      // -1: no such probe column (never above)
     }
-#pragma unroll 1
-    for (int i = 0; i < PROBE_PPT; ++i) {
-        const int k = g * PROBE_PPT + i;
-        if (k >= a.n_probes) break;
-        if (!above(c0[i], thr, avg, snr)) continue;
+    unsigned hits = 0;
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) hits |= (c0[i] >= 0.f && above(c0[i], thr, avg, snr)) ? (1u << i) : 0u;
+    while (hits) {
+        const int i = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const int k = g * PPT + i;
         const int ti = k * a.stride;
         float lo_c[PROBE_QUICK], hi_c[PROBE_QUICK];
 #pragma unroll
@@ -305,8 +316,10 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-template <int TILE>
-__global__ void extract_kernel(ScanArgs a) {
+// MINB > 0: 128-thread CTAs with at least MINB of them resident per SM (register cap), so that one wave of warps covers the
+// work list: every item is one chain of dependent memory round trips, a second wave doubles the kernel time
+template <int TILE, int MINB>
+__global__ void __launch_bounds__(MINB > 0 ? 128 : 1024, MINB > 0 ? MINB : 1) extract_kernel(ScanArgs a) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -463,7 +476,9 @@ struct rt_engine {
     uint4* d_bmat = nullptr;                 // tensor-core operand image
     rt::TcTables tc_tab;
     int tc_grid = 0, tc_slots = 1, tc_bps = 0;
-    int probe_threads = 256, extract_threads = 128, extract_ctas = 148 * 16;   // scan launch shapes (RT_SCAN_SHAPE=probe,extract,ctas)
+    int extract_minb = 0;                    // RT_EXTRACT_MINB: 0 (no register cap), 12 or 16 resident 128-thread CTAs per SM
+    int probe_ppt = PROBE_PPT;               // probe columns per thread: 8, 16 or 32 (RT_PROBE_PPT)
+    int probe_threads = 256, extract_threads = 128, extract_ctas = 148 * 24;   // scan launch shapes (RT_SCAN_SHAPE=probe,extract,ctas)
     float* d_win = nullptr;
     float2* d_tw = nullptr;
     // three spectrogram buffers: launch i writes S[i % 3] while the scan of launch i-1 still reads
@@ -580,7 +595,7 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     if (cfg->cuda_device < 0 || cfg->cuda_device >= ndev) return fail(RT_ERR_CUDA, "no such CUDA device (this engine has no CPU fallback)");
     CU(cudaSetDevice(cfg->cuda_device));
     cudaFuncAttributes fa;
-    cudaError_t ferr = cudaFuncGetAttributes(&fa, probe_kernel<LAYOUT_PERM>);
+    cudaError_t ferr = cudaFuncGetAttributes(&fa, probe_kernel<LAYOUT_PERM, PROBE_PPT>);
     if (ferr != cudaSuccess)
         return fail(RT_ERR_CUDA, std::string("kernels not loadable on this device (built for sm_100a only): ") + cudaGetErrorString(ferr));
 
@@ -603,6 +618,8 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
         e->chunk_segs = e->T >= 4096 ? 256 : (e->T >= 2048 ? 128 : 64);
     }
     if (const char* cs = std::getenv("RT_CHUNK_SEGS")) { const int v = std::atoi(cs); if (e->reg256 && v >= 8 && v % 8 == 0) e->chunk_segs = v; }
+    if (const char* mb = std::getenv("RT_EXTRACT_MINB")) { const int v = std::atoi(mb); if (v == 0 || v == 12 || v == 16) e->extract_minb = v; }
+    if (const char* pp = std::getenv("RT_PROBE_PPT")) { const int v = std::atoi(pp); if (v == 8 || v == 16 || v == 32) e->probe_ppt = v; }
     if (const char* sh = std::getenv("RT_SCAN_SHAPE")) {
         int a = 0, b = 0, c = 0;
         if (std::sscanf(sh, "%d,%d,%d", &a, &b, &c) == 3 && a >= 32 && a <= 1024 && a % 32 == 0 && b >= 32 && b <= 1024 && b % 32 == 0 && c >= 1) { e->probe_threads = a; e->extract_threads = b; e->extract_ctas = c; }
@@ -844,28 +861,44 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     if (evs) CU(cudaEventRecord(evs->ev[2], sc_st));
     const bool sep_mean = !(use_reg && e->tc256) && e->n_chunks > 64;
     if (sep_mean) {
-        row_mean_kernel<<<dim3((e->n + 127) / 128, e->n_streams), 128, 0, sc_st>>>(e->d_part[slot], e->d_avg[slot], e->n, e->n_chunks, e->T);
+        row_mean_kernel<<<dim3((e->n + 127) / 128, e->n_streams), 128, 0, sc_st>>>(e->d_part[slot], e->d_avg[slot], e->n, e->n_chunks, e->T, (use_reg && !e->tc256) ? 1 : 0);
         CU(cudaGetLastError());
     }
     if (evs) CU(cudaEventRecord(evs->ev[3], sc_st));
 
     ScanArgs sc;
-    sc.S = e->d_S[next]; sc.Sprev = e->d_S[e->cur]; sc.stream_stride = e->s_stride; sc.avg = e->d_avg[slot]; sc.part = ((use_reg && e->tc256) || sep_mean) ? nullptr : e->d_part[slot]; sc.n_chunks = e->n_chunks; sc.thr = e->d_thr; sc.has_prev = e->d_hasprev;
+    sc.S = e->d_S[next]; sc.Sprev = e->d_S[e->cur]; sc.stream_stride = e->s_stride; sc.avg = e->d_avg[slot]; sc.part = ((use_reg && e->tc256) || sep_mean) ? nullptr : e->d_part[slot]; sc.n_chunks = e->n_chunks; sc.part_perm = (use_reg && !e->tc256) ? 1 : 0; sc.thr = e->d_thr; sc.has_prev = e->d_hasprev;
     sc.snr = (float)e->cfg.snr_threshold;
     sc.n = e->n; sc.T = e->T; sc.stride = e->cfg.probe_stride; sc.n_probes = e->n_probes;
     sc.min_cols = e->cfg.min_cols; sc.max_cols = e->cfg.max_cols;
     sc.work = e->d_work; sc.counters = d_cnt; sc.rec = e->d_rec[slot]; sc.max_records = e->cfg.max_records;
     const int pth = e->probe_threads, eth = e->extract_threads, ect = e->extract_ctas;
     const int pbins = std::min(e->n, pth);
-    dim3 pgrid(((e->n + pbins - 1) / pbins) * ((e->n_probes + PROBE_PPT - 1) / PROBE_PPT), e->n_streams);
-    if (use_reg && e->tc256) probe_kernel<LAYOUT_TILE><<<pgrid, pbins, 0, sc_st>>>(sc);
-    else if (use_reg) probe_kernel<LAYOUT_PERM><<<pgrid, pbins, 0, sc_st>>>(sc);
-    else probe_kernel<LAYOUT_LINEAR><<<pgrid, pbins, 0, sc_st>>>(sc);
+    const int ppt = e->probe_ppt;
+    dim3 pgrid(((e->n + pbins - 1) / pbins) * ((e->n_probes + ppt - 1) / ppt), e->n_streams);
+#define RT_PROBE(L)                                                                        \
+    do {                                                                                   \
+        if (ppt == 8) probe_kernel<L, 8><<<pgrid, pbins, 0, sc_st>>>(sc);                  \
+        else if (ppt == 16) probe_kernel<L, 16><<<pgrid, pbins, 0, sc_st>>>(sc);           \
+        else probe_kernel<L, 32><<<pgrid, pbins, 0, sc_st>>>(sc);                          \
+    } while (0)
+    if (use_reg && e->tc256) RT_PROBE(LAYOUT_TILE);
+    else if (use_reg) RT_PROBE(LAYOUT_PERM);
+    else RT_PROBE(LAYOUT_LINEAR);
+#undef RT_PROBE
     CU(cudaGetLastError());
     if (evs) CU(cudaEventRecord(evs->ev[4], sc_st));
-    if (use_reg && e->tc256) extract_kernel<LAYOUT_TILE><<<ect, eth, 0, sc_st>>>(sc);
-    else if (use_reg) extract_kernel<LAYOUT_PERM><<<ect, eth, 0, sc_st>>>(sc);
-    else extract_kernel<LAYOUT_LINEAR><<<ect, eth, 0, sc_st>>>(sc);
+    const int emb = eth == 128 ? e->extract_minb : 0;
+#define RT_EXTRACT(L)                                                                      \
+    do {                                                                                   \
+        if (emb == 16) extract_kernel<L, 16><<<ect, eth, 0, sc_st>>>(sc);                  \
+        else if (emb == 12) extract_kernel<L, 12><<<ect, eth, 0, sc_st>>>(sc);             \
+        else extract_kernel<L, 0><<<ect, eth, 0, sc_st>>>(sc);                             \
+    } while (0)
+    if (use_reg && e->tc256) RT_EXTRACT(LAYOUT_TILE);
+    else if (use_reg) RT_EXTRACT(LAYOUT_PERM);
+    else RT_EXTRACT(LAYOUT_LINEAR);
+#undef RT_EXTRACT
     CU(cudaGetLastError());
     if (evs) CU(cudaEventRecord(evs->ev[5], sc_st));
 

@@ -23,7 +23,7 @@ struct SpectroArgs {
     const float2* tw;      // exp(-2 pi i k / n)
     float* S;              // generic kernel: [stream][T][n]; register kernel: [stream][T][pos(bin)] (see rt_engine.cu)
     size_t S_stream_stride;  // floats per stream
-    float* part;           // [stream][chunk][n]   (FFT bin order)
+    float* part;           // [stream][chunk][n]   (FFT bin order; spectro_reg256_v7: PERM position order, like its S rows)
 };
 
 // compile-time variant selection
@@ -588,12 +588,13 @@ __global__ void __launch_bounds__(R256v7::THREADS, MINB) spectro_reg256_v7(Spect
 #pragma unroll
     for (int k2 = 0; k2 < 16; ++k2) red[hw * 256 + 16 * k2 + j] = acc[k2];
     __syncthreads();
+    // written in the order of the S rows (PERM position, see rt_engine.cu) so that the probe kernel reads both coalesced
     float* pd = a.part + ((size_t)s * a.n_chunks + blockIdx.x) * 256;
     for (int fi = tid; fi < 256; fi += C::THREADS) {
         float t = 0.f;
 #pragma unroll
         for (int hh = 0; hh < 2 * C::WARPS; ++hh) t += red[hh * 256 + fi];
-        pd[fi] = t;
+        pd[((fi >> 6) << 6) | ((fi & 15) << 2) | ((fi >> 4) & 3)] = t;
     }}
 
 }  // namespace rt

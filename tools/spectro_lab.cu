@@ -81,7 +81,8 @@ void run_k(Ctx& c, kern_t kern, int THREADS, int SMEM, const char* name, int chu
     std::vector<float> rows((size_t)c.streams * 256, 0.f);
     for (int s = 0; s < c.streams; ++s)
         for (int ch = 0; ch < a.n_chunks; ++ch)
-            for (int fi = 0; fi < 256; ++fi) rows[s * 256 + fi] += part[((size_t)s * a.n_chunks + ch) * 256 + fi];
+            for (int fi = 0; fi < 256; ++fi)      // spectro_reg256_v7 writes its chunk sums in PERM position order
+                rows[s * 256 + fi] += part[((size_t)s * a.n_chunks + ch) * 256 + (strncmp(name, "v7", 2) == 0 ? (((fi >> 6) << 6) | ((fi & 15) << 2) | ((fi >> 4) & 3)) : fi)];
     double maxrel = 0;
     if (c.ref.empty()) c.ref = rows;
     else for (size_t i = 0; i < rows.size(); ++i) maxrel = std::max(maxrel, (double)std::fabs(rows[i] - c.ref[i]) / (std::fabs(c.ref[i]) + 1e-30));

@@ -174,7 +174,7 @@ int main(int argc, char** argv) {
     for (int s = 0; s < streams; ++s)
         for (int fi = 0; fi < 256; ++fi) {
             double r7 = 0, rt_ = 0;
-            for (int c = 0; c < n_chunks; ++c) r7 += p7[((size_t)s * n_chunks + c) * 256 + fi];
+            for (int c = 0; c < n_chunks; ++c) r7 += p7[((size_t)s * n_chunks + c) * 256 + perm_pos(fi)];     // v7 writes its chunk sums in PERM order
             for (int c = 0; c < slots; ++c) rt_ += pt[((size_t)s * slots + c) * 256 + fi];
             rt_ /= tab.pscale;
             const double rel = fabs(rt_ - r7) / (fabs(r7) + 1e-300);
