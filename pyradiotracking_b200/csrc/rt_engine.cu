@@ -189,26 +189,43 @@ __global__ void __launch_bounds__(NT) spectro_generic(SpectroArgs a) {
 // ---------------------------------------------------------------------------------------------
 // fixed summation order (4 interleaved partial sums over the chunks), float64: run-to-run identical and
 // identical in every CTA that evaluates it
+template <bool LEAN = false>
 __device__ __forceinline__ float row_mean_of(const float* part, int s, int fi, int n, int n_chunks, int T) {
     const float* p = part + (size_t)s * n_chunks * n + fi;
     double t[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int c0 = 0; c0 < n_chunks; c0 += 16) {          // 16 chunk sums per memory round trip
-        float v[16];
+    if (LEAN) {                                          // 32-register kernels: 8 chunk sums per round trip, same summation order
+        for (int c0 = 0; c0 < n_chunks; c0 += 8) {
+            float v[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = (c0 + i < n_chunks) ? p[(size_t)(c0 + i) * n] : 0.f;
+            for (int i = 0; i < 8; ++i) v[i] = (c0 + i < n_chunks) ? p[(size_t)(c0 + i) * n] : 0.f;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) t[i & 3] += (double)v[i];
+            for (int i = 0; i < 8; ++i) t[i & 3] += (double)v[i];
+        }
+    } else if (n_chunks <= 48) {                                // the usual case: every chunk sum in flight at once (one round trip)
+        float v[48];
+#pragma unroll
+        for (int i = 0; i < 48; ++i) v[i] = (i < n_chunks) ? p[(size_t)i * n] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 48; ++i) t[i & 3] += (double)v[i];     // + 0.0 beyond n_chunks: same value as the loop below
+    } else {
+        for (int c0 = 0; c0 < n_chunks; c0 += 16) {      // 16 chunk sums per memory round trip
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = (c0 + i < n_chunks) ? p[(size_t)(c0 + i) * n] : 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) t[i & 3] += (double)v[i];
+        }
     }
     return (float)(((t[0] + t[1]) + (t[2] + t[3])) / (double)T);
 }
 
 // stand-alone row means for kernels that leave many partial rows per stream (spectro_r16: one per CTA): the probe
 // kernel's prologue would repeat the long reduction in every probe group
-__global__ void row_mean_kernel(const float* part, float* avg, int n, int n_chunks, int T, int part_perm) {
+__global__ void __launch_bounds__(128, 16) row_mean_kernel(const float* part, float* avg, int n, int n_chunks, int T, int part_perm) {
     const int fi = blockIdx.x * blockDim.x + threadIdx.x;
     // part_perm: the register kernel writes its chunk sums in PERM position order (n == 256)
     const int src = part_perm ? (((fi >> 6) << 6) | ((fi & 15) << 2) | ((fi >> 4) & 3)) : fi;
-    if (fi < n) avg[blockIdx.y * n + fi] = row_mean_of(part, blockIdx.y, src, n, n_chunks, T);
+    if (fi < n) avg[blockIdx.y * n + fi] = row_mean_of<true>(part, blockIdx.y, src, n, n_chunks, T);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -217,6 +234,7 @@ __global__ void row_mean_kernel(const float* part, float* avg, int n, int n_chun
 struct ScanArgs {
     const float* S;        // current block (LINEAR or TILE layout)
     const float* Sprev;    // previous block
+    const float* P;        // probe plane [stream][n_probes][256] in PERM order (register kernel), or nullptr: probe S itself
     size_t stream_stride;  // floats per stream
     float* avg;            // [stream][n] row means: written by the probe kernel (from `part`) or by the tensor-core kernel
     const float* part;     // [stream][n_chunks][n] chunk row sums (nullptr: avg is already there)
@@ -226,82 +244,209 @@ struct ScanArgs {
     const int* has_prev;   // [stream]
     float snr;
     int n, T, stride, n_probes, min_cols, max_cols;
-    uint2* work;           // (stream << 16 | fi, ti)
+    int n_streams_scan;    // streams of the batch (lean probe kernel: tiles are walked with a grid stride)
+    uint2* work;           // (stream << 16 | fi, ti | (chain members - 1) << 24): consecutive probe columns ti, ti + stride, ...
     int* counters;         // [0] work items, [1] records
     rt_record* rec;
     int max_records;
 };
 
 constexpr int PROBE_QUICK = 3;   // cells examined on each side before handing a probe hit to a warp
-constexpr int EX_W = 4;          // 32-cell windows an extraction warp examines per memory round trip
+constexpr int PROBE_CHAIN = 8;   // consecutive surviving probe hits of a bin handed to ONE extraction warp (bounds its serial work)
+// extraction kernel: EX_W 32-cell windows per memory round trip, EX_F forward windows fetched together with the backward
+// window in a work item's first round trip (template parameters: 4 / 4 stand-alone, 2 / 2 for the 32-register lean variant)
 
 constexpr int PROBE_PPT = 32;    // probe columns per thread: their loads are in flight together, and the row-mean prologue
                                  // is repeated once per PROBE_PPT columns (8 -> 32: 5x fewer instructions, 29 -> see DESIGN 5.4)
 
+constexpr int PROBE_LIST = 2048; // probe hits a CTA resolves in parallel (more than that: resolved by the finding thread itself)
+
 // One thread per (stream, bin, group of PPT probe columns); blockDim.x bins of one stream per CTA.
 // Prologue: the bin's row mean from the chunk sums (analyze.py:374-375) -- every CTA of the stream computes the
 // same value, the CTAs of probe group 0 publish it for the extraction kernel and the parity hook.
+// Three phases, each ONE memory round trip: (1) chunk sums + probe cells of every thread, (2) the CTA's hits are pooled in
+// shared memory and resolved one per thread (the neighbours of a hit), (3) every thread chains its surviving hits.
 template <int TILE, int PPT>
 __global__ void probe_kernel(ScanArgs a) {
     static_assert(PPT >= 1 && PPT <= 32, "hit mask is one word");
+    __shared__ float s_avg[1024];
+    __shared__ unsigned s_live[1024];
+    __shared__ unsigned s_list[PROBE_LIST];
+    __shared__ int s_n;
+    const int tid = threadIdx.x;
     const int nbb = (a.n + blockDim.x - 1) / blockDim.x;           // bin blocks
     const int bb = blockIdx.x % nbb, g = blockIdx.x / nbb;
-    const int idx = bb * blockDim.x + threadIdx.x;
+    const int idx = bb * blockDim.x + tid;
     const int s = blockIdx.y;
-    if (idx >= a.n) return;
+    const bool active = idx < a.n;
     // PERM layout: the thread index is the position inside the S row (and inside the chunk-sum rows, which the register
     // kernel writes in the same order), so a warp reads 128 contiguous bytes per load instead of 2 floats out of each of
     // 8 sectors; position 64 a + 4 k1 + b holds bin k1 + 16 (4 a + b)
-    const int fi = TILE == LAYOUT_PERM ? ((idx >> 2) & 15) + 16 * (4 * (idx >> 6) + (idx & 3)) : idx;
-    float avg;
-    if (a.part != nullptr) {
-        avg = row_mean_of(a.part, s, a.part_perm ? idx : fi, a.n, a.n_chunks, a.T);
-        if (g == 0) a.avg[s * a.n + fi] = avg;
-    } else {
-        avg = a.avg[s * a.n + fi];
-    }
-    const CellRef col = CellRef::make<TILE>(a.S, a.stream_stride, s, fi, a.n);
+    auto bin_of = [](int ix) { return TILE == LAYOUT_PERM ? ((ix >> 2) & 15) + 16 * (4 * (ix >> 6) + (ix & 3)) : ix; };
+    const int fi = bin_of(idx);
     const float thr = a.thr[s], snr = a.snr;
-    // ~96 % of the probe cells fail the predicate: only a hit pays for its neighbours
-    float c0[PPT];
-#pragma unroll
-    for (int i = 0; i < PPT; ++i) {
-        const int k = g * PPT + i;
-        c0[i] = (k < a.n_probes) ? col.at<TILE>(k * a.stride) : -1.f;      // -1: no such probe column (never above)
-    }
+    if (tid == 0) s_n = 0;
+    s_live[tid] = 0;
+    float avg = 1.f;
     unsigned hits = 0;
+    if (active) {
+        // ~96 % of the probe cells fail the predicate: only a hit pays for its neighbours
+        float c0[PPT];
+        if (TILE == LAYOUT_PERM && a.P != nullptr) {
+            // the register kernel left a dense copy of the probe columns: a warp reads 128 contiguous bytes per load
+            const float* prow = a.P + ((size_t)s * a.n_probes + (size_t)g * PPT) * 256 + idx;
 #pragma unroll
-    for (int i = 0; i < PPT; ++i) hits |= (c0[i] >= 0.f && above(c0[i], thr, avg, snr)) ? (1u << i) : 0u;
-    while (hits) {
-        const int i = __ffs(hits) - 1;
-        hits &= hits - 1;
-        const int k = g * PPT + i;
-        const int ti = k * a.stride;
+            for (int i = 0; i < PPT; ++i) c0[i] = (g * PPT + i < a.n_probes) ? prow[(size_t)i * 256] : -1.f;
+        } else {
+            const CellRef col = CellRef::make<TILE>(a.S, a.stream_stride, s, fi, a.n);
+#pragma unroll
+            for (int i = 0; i < PPT; ++i) {
+                const int k = g * PPT + i;
+                c0[i] = (k < a.n_probes) ? col.at<TILE>(k * a.stride) : -1.f;      // -1: no such probe column (never above)
+            }
+        }
+        if (a.part != nullptr) {
+            avg = row_mean_of(a.part, s, a.part_perm ? idx : fi, a.n, a.n_chunks, a.T);
+            if (g == 0) a.avg[s * a.n + fi] = avg;
+        } else {
+            avg = a.avg[s * a.n + fi];
+        }
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) hits |= (c0[i] >= 0.f && above(c0[i], thr, avg, snr)) ? (1u << i) : 0u;
+    }
+    s_avg[tid] = avg;
+    __syncthreads();
+
+    // Most hits are 1-2 cell noise runs that the duration gate rejects anyway: resolve those here.  true = hand it to a warp
+    auto resolve = [&](int fi_, float avg_, int i) -> bool {
+        const CellRef col = CellRef::make<TILE>(a.S, a.stream_stride, s, fi_, a.n);
+        const int ti = (g * PPT + i) * a.stride;
         float lo_c[PROBE_QUICK], hi_c[PROBE_QUICK];
 #pragma unroll
         for (int d = 1; d <= PROBE_QUICK; ++d) {
             lo_c[d - 1] = (ti - d >= 0) ? col.at<TILE>(ti - d) : 0.f;
             hi_c[d - 1] = (ti + d < a.T) ? col.at<TILE>(ti + d) : 0.f;
         }
-        // Most hits are 1-2 cell noise runs that the duration gate rejects anyway: resolve those here.
         int lo = -1, hi = -1;             // nearest not-above cells, if found within PROBE_QUICK
-        bool drop = false;
 #pragma unroll
         for (int d = 1; d <= PROBE_QUICK; ++d) {
             const int t = ti - d;
             if (t < 0) break;             // run reaches column 0: carry logic, leave it to the warp
-            if (!above(lo_c[d - 1], thr, avg, snr)) { lo = t; break; }
+            if (!above(lo_c[d - 1], thr, avg_, snr)) { lo = t; break; }
         }
 #pragma unroll
         for (int d = 1; d <= PROBE_QUICK; ++d) {
             const int t = ti + d;
-            if (t >= a.T) { drop = true; break; }     // run touches the block end: dropped (analyze.py:415-417)
-            if (!above(hi_c[d - 1], thr, avg, snr)) { hi = t; break; }
+            if (t >= a.T) return false;   // run touches the block end: dropped (analyze.py:415-417)
+            if (!above(hi_c[d - 1], thr, avg_, snr)) { hi = t; break; }
         }
-        if (drop) continue;
-        if (lo >= 0 && hi >= 0 && hi - lo < a.min_cols) continue;   // window = [lo, hi): too short
+        return !(lo >= 0 && hi >= 0 && hi - lo < a.min_cols);      // window = [lo, hi): too short
+    };
+
+    unsigned live = 0;
+    while (hits) {
+        const int i = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const int slot = atomicAdd(&s_n, 1);
+        if (slot < PROBE_LIST) s_list[slot] = ((unsigned)tid << 5) | (unsigned)i;
+        else if (resolve(fi, avg, i)) live |= 1u << i;
+    }
+    __syncthreads();
+    const int n_list = min(s_n, PROBE_LIST);
+    for (int e = tid; e < n_list; e += blockDim.x) {
+        const unsigned ent = s_list[e];
+        const int o = (int)(ent >> 5), i = (int)(ent & 31u);
+        if (resolve(bin_of(bb * blockDim.x + o), s_avg[o], i)) atomicOr(&s_live[o], 1u << i);
+    }
+    __syncthreads();
+    live |= s_live[tid];
+    // Surviving hits at consecutive probe columns almost always lie in the same run (a pulse of 75-375 columns spans
+    // 1-5 probes at config 2): they form one work item (head column + length, at most PROBE_CHAIN members), and the
+    // extraction warp walks the members the way the reference's probe loop does (ti_skip, analyze.py:366).
+    while (live) {
+        const int head = __ffs(live) - 1;
+        int len = 1;
+        while (head + len < 32 && ((head + len) % PROBE_CHAIN) != 0 && ((live >> (head + len)) & 1u)) ++len;
+        live &= ~(((1u << len) - 1u) << head);
         const int slot = atomicAdd(&a.counters[0], 1);
-        a.work[slot] = make_uint2(((unsigned)s << 16) | (unsigned)fi, (unsigned)ti);
+        a.work[slot] = make_uint2(((unsigned)s << 16) | (unsigned)fi, (unsigned)((g * PPT + head) * a.stride) | ((unsigned)(len - 1) << 24));
+    }
+}
+
+// Lean variant for the two-stream schedule.  The register kernel keeps 4 CTAs x 128 threads x 120 registers resident per SM,
+// which leaves exactly 4096 registers: a 128-thread CTA capped at 32 registers runs BESIDE them instead of waiting for (and
+// then displacing) a spectrogram CTA.  One such CTA per SM walks the (stream, probe group, position block) tiles with a grid
+// stride; 8 probe columns per thread and tile, hits resolved by the finding thread; row means come from row_mean_kernel.
+constexpr int LEAN_PPT = 8;
+static_assert(LEAN_PPT == PROBE_CHAIN, "a chain must not leave its tile");
+template <int TILE>
+__global__ void __launch_bounds__(128, 16) probe_lean_kernel(ScanArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * 4 + (threadIdx.x >> 5), n_warps = gridDim.x * 4;
+    const int npb = (a.n + 31) / 32, ngr = (a.n_probes + LEAN_PPT - 1) / LEAN_PPT;
+    const int n_tiles = npb * ngr * a.n_streams_scan;
+    const float snr = a.snr;
+    // a tile = 32 row positions x 8 probe columns of one stream; the warps walk the tiles independently (no CTA barrier)
+    for (int tile = warp; tile < n_tiles; tile += n_warps) {
+        const int pb = tile % npb, g = (tile / npb) % ngr, s = tile / (npb * ngr);
+        const int idx = pb * 32 + lane;
+        if (idx >= a.n) continue;
+        const int fi = TILE == LAYOUT_PERM ? ((idx >> 2) & 15) + 16 * (4 * (idx >> 6) + (idx & 3)) : idx;
+        const CellRef col = CellRef::make<TILE>(a.S, a.stream_stride, s, fi, a.n);
+        float c0[LEAN_PPT];
+        if (TILE == LAYOUT_PERM && a.P != nullptr) {
+            const float* prow = a.P + ((size_t)s * a.n_probes + (size_t)g * LEAN_PPT) * 256 + idx;
+#pragma unroll
+            for (int i = 0; i < LEAN_PPT; ++i) c0[i] = (g * LEAN_PPT + i < a.n_probes) ? prow[(size_t)i * 256] : -1.f;
+        } else {
+#pragma unroll
+            for (int i = 0; i < LEAN_PPT; ++i) {
+                const int k = g * LEAN_PPT + i;
+                c0[i] = (k < a.n_probes) ? col.at<TILE>(k * a.stride) : -1.f;
+            }
+        }
+        const float thr = a.thr[s], avg = a.avg[s * a.n + fi];
+        unsigned hits = 0;
+#pragma unroll
+        for (int i = 0; i < LEAN_PPT; ++i) hits |= (c0[i] >= 0.f && above(c0[i], thr, avg, snr)) ? (1u << i) : 0u;
+        int head = -1, len = 0;              // open chain (LEAN_PPT == PROBE_CHAIN: a chain never leaves the tile)
+        auto flush = [&]() {
+            if (len > 0) {
+                const int slot = atomicAdd(&a.counters[0], 1);
+                a.work[slot] = make_uint2(((unsigned)s << 16) | (unsigned)fi, (unsigned)((g * LEAN_PPT + head) * a.stride) | ((unsigned)(len - 1) << 24));
+            }
+            len = 0;
+        };
+        while (hits) {
+            const int i = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const int ti = (g * LEAN_PPT + i) * a.stride;
+            float lo_c[PROBE_QUICK], hi_c[PROBE_QUICK];          // one round trip for the six neighbours
+#pragma unroll
+            for (int d = 1; d <= PROBE_QUICK; ++d) {
+                lo_c[d - 1] = (ti - d >= 0) ? col.at<TILE>(ti - d) : 0.f;
+                hi_c[d - 1] = (ti + d < a.T) ? col.at<TILE>(ti + d) : 0.f;
+            }
+            bool keep = true;
+            int lo = -1, hi = -1;
+#pragma unroll
+            for (int d = 1; d <= PROBE_QUICK; ++d) {
+                const int t = ti - d;
+                if (t < 0) break;
+                if (!above(lo_c[d - 1], thr, avg, snr)) { lo = t; break; }
+            }
+#pragma unroll
+            for (int d = 1; d <= PROBE_QUICK; ++d) {
+                const int t = ti + d;
+                if (t >= a.T) { keep = false; break; }
+                if (!above(hi_c[d - 1], thr, avg, snr)) { hi = t; break; }
+            }
+            if (keep && lo >= 0 && hi >= 0 && hi - lo < a.min_cols) keep = false;
+            if (keep && len > 0 && i == head + len) { ++len; continue; }
+            flush();
+            if (keep) { head = i; len = 1; }
+        }
+        flush();
     }
 }
 
@@ -318,7 +463,7 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // MINB > 0: 128-thread CTAs with at least MINB of them resident per SM (register cap), so that one wave of warps covers the
 // work list: every item is one chain of dependent memory round trips, a second wave doubles the kernel time
-template <int TILE, int MINB>
+template <int TILE, int MINB, int EX_W = 4, int EX_F = 4>
 __global__ void __launch_bounds__(MINB > 0 ? 128 : 1024, MINB > 0 ? MINB : 1) extract_kernel(ScanArgs a) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -328,17 +473,41 @@ __global__ void __launch_bounds__(MINB > 0 ? 128 : 1024, MINB > 0 ? MINB : 1) ex
 
     for (int item = warp; item < n_work; item += n_warps) {
         const uint2 wk = a.work[item];
-        const int s = wk.x >> 16, fi = wk.x & 0xffff, ti = (int)wk.y;
+        const int s = wk.x >> 16, fi = wk.x & 0xffff, ti0 = (int)(wk.y & 0xffffffu), members = (int)(wk.y >> 24) + 1;
         const CellRef col = CellRef::make<TILE>(a.S, a.stream_stride, s, fi, n);
         const CellRef pcol = CellRef::make<TILE>(a.Sprev, a.stream_stride, s, fi, n);
         const float thr = a.thr[s], avg = a.avg[s * n + fi], snr = a.snr;
+        int skip_to = 0;                                 // every cell in [previous member's probe, skip_to) is known to be above
+      for (int mem = 0; mem < members; ++mem) {
+        const int ti = ti0 + mem * a.stride;
+        if (ti < skip_to) continue;                      // inside the run the previous member evaluated (ti_skip, analyze.py:366)
 
-        // ---- backward: nearest not-above cell in [ti - stride, ti).  If there is none and the
-        // previous probe column exists, that probe already owns this run (ti_skip, analyze.py:366).
-        // Every walk looks at EX_W * 32 cells per memory round trip.
+        // ---- round 1: the backward window [ti - stride, ti) and the first forward windows are independent loads: one memory
+        // round trip for both (after the probe kernel's chaining most work items own their run, so the forward cells are
+        // rarely wasted).  Backward: nearest not-above cell; if there is none and the previous probe column exists, that
+        // probe already owns this run (ti_skip, analyze.py:366).
         const int lo_lim = max(ti - a.stride, 0);
+        float pb[EX_W], pf[EX_F];
+#pragma unroll
+        for (int w = 0; w < EX_W; ++w) {
+            const int t = ti - 1 - 32 * w - lane;
+            pb[w] = (t >= lo_lim) ? col.at<TILE>(t) : -1.f;          // -1: outside the window
+        }
+#pragma unroll
+        for (int w = 0; w < EX_F; ++w) {
+            const int t = ti + 1 + 32 * w + lane;
+            pf[w] = (t < T) ? col.at<TILE>(t) : -1.f;
+        }
         int nb = -1;
-        for (int base = ti - 1; base >= lo_lim && nb < 0; base -= 32 * EX_W) {
+        {
+            unsigned m[EX_W];
+#pragma unroll
+            for (int w = 0; w < EX_W; ++w) m[w] = __ballot_sync(0xffffffffu, pb[w] >= 0.f && !above(pb[w], thr, avg, snr));
+#pragma unroll
+            for (int w = 0; w < EX_W; ++w)
+                if (nb < 0 && m[w]) nb = ti - 1 - 32 * w - (__ffs(m[w]) - 1);
+        }
+        for (int base = ti - 1 - 32 * EX_W; base >= lo_lim && nb < 0; base -= 32 * EX_W) {     // probe strides > 32 EX_W only
             unsigned m[EX_W];
 #pragma unroll
             for (int w = 0; w < EX_W; ++w) {
@@ -382,12 +551,23 @@ __global__ void __launch_bounds__(MINB > 0 ? 128 : 1024, MINB > 0 ? MINB : 1) ex
             else continue;                               // longer than max_cols: fails the duration test
         }
 
-        // ---- forward: first not-above cell after ti (analyze.py:401-412)
+        // ---- forward: first not-above cell after ti (analyze.py:401-412); the first EX_F windows are already here
         int end = -1;
         const int span_cap = a.max_cols + 2;             // beyond this the duration test fails anyway
         bool too_long = false;
-        for (int base = ti + 1; base < T && end < 0; base += 32 * EX_W) {
-            if (base - start > span_cap) { too_long = true; break; }
+        if (ti + 1 < T) {
+            if (ti + 1 - start > span_cap) { too_long = true; skip_to = ti + 1; }
+            else {
+                unsigned m[EX_F];
+#pragma unroll
+                for (int w = 0; w < EX_F; ++w) m[w] = __ballot_sync(0xffffffffu, pf[w] >= 0.f && !above(pf[w], thr, avg, snr));
+#pragma unroll
+                for (int w = 0; w < EX_F; ++w)
+                    if (end < 0 && m[w]) end = ti + 1 + 32 * w + (__ffs(m[w]) - 1);
+            }
+        }
+        for (int base = ti + 1 + 32 * EX_F; base < T && end < 0 && !too_long; base += 32 * EX_W) {
+            if (base - start > span_cap) { too_long = true; skip_to = base; break; }
             unsigned m[EX_W];
 #pragma unroll
             for (int w = 0; w < EX_W; ++w) {
@@ -400,7 +580,11 @@ __global__ void __launch_bounds__(MINB > 0 ? 128 : 1024, MINB > 0 ? MINB : 1) ex
             for (int w = 0; w < EX_W; ++w)
                 if (end < 0 && m[w]) end = base + 32 * w + (__ffs(m[w]) - 1);
         }
-        if (too_long || end < 0) continue;               // end == T: dropped, re-found from the next block
+        if (too_long || end < 0) {                       // end == T: dropped, re-found from the next block
+            if (!too_long) skip_to = T;
+            continue;
+        }
+        skip_to = end;
         const int cols = end - start + (start < 0 ? 1 : 0);
         if (cols < a.min_cols || cols > a.max_cols) continue;
 
@@ -442,6 +626,7 @@ __global__ void __launch_bounds__(MINB > 0 ? 128 : 1024, MINB > 0 ? MINB : 1) ex
                 a.rec[slot] = r;
             }
         }
+      }
     }
 }
 
@@ -479,6 +664,9 @@ struct rt_engine {
     int extract_minb = 0;                    // RT_EXTRACT_MINB: 0 (no register cap), 12 or 16 resident 128-thread CTAs per SM
     int probe_ppt = PROBE_PPT;               // probe columns per thread: 8, 16 or 32 (RT_PROBE_PPT)
     int probe_threads = 256, extract_threads = 128, extract_ctas = 148 * 24;   // scan launch shapes (RT_SCAN_SHAPE=probe,extract,ctas)
+    int v7_maxr = 112;                       // register cap of the register kernel (RT_V7_MAXR)
+    bool scan_lean = false;                  // two-stream schedule: 32-register scan CTAs that fit beside the resident spectrogram CTAs
+    int lean_ctas = 148;
     float* d_win = nullptr;
     float2* d_tw = nullptr;
     // three spectrogram buffers: launch i writes S[i % 3] while the scan of launch i-1 still reads
@@ -486,6 +674,7 @@ struct rt_engine {
     float* d_S[RT_SBUFS] = {nullptr, nullptr, nullptr};
     int cur = 0;
     float* d_part[2] = {nullptr, nullptr};   // chunk row sums, by launch parity
+    float* d_probe[2] = {nullptr, nullptr};  // probe plane (register kernel), by launch parity
     cudaStream_t scan_stream = nullptr;      // row mean / probe / extract: overlaps the next launch's spectrogram
     cudaEvent_t spec_done[2] = {nullptr, nullptr};
     float* d_avg[2] = {nullptr, nullptr};    // row means, by launch parity (written by the spectrogram kernel)
@@ -548,7 +737,7 @@ void free_engine(rt_engine* e) {
         for (auto& ev : s.ev) cudaEventDestroy(ev);
     cudaFree(e->d_win); cudaFree(e->d_tw);
     for (auto& p : e->d_S) cudaFree(p);
-    cudaFree(e->d_part[0]); cudaFree(e->d_part[1]); cudaFree(e->d_avg[0]); cudaFree(e->d_avg[1]); cudaFree(e->d_ctr); cudaFree(e->d_bmat); cudaFree(e->d_thr); cudaFree(e->d_hasprev);
+    cudaFree(e->d_part[0]); cudaFree(e->d_part[1]); cudaFree(e->d_probe[0]); cudaFree(e->d_probe[1]); cudaFree(e->d_avg[0]); cudaFree(e->d_avg[1]); cudaFree(e->d_ctr); cudaFree(e->d_bmat); cudaFree(e->d_thr); cudaFree(e->d_hasprev);
     cudaFree(e->d_stage[0]); cudaFree(e->d_stage[1]); cudaFree(e->d_work);
     for (int k = 0; k < 2; ++k) { if (e->h2d_done[k]) cudaEventDestroy(e->h2d_done[k]); if (e->stage_free[k]) cudaEventDestroy(e->stage_free[k]); }
     if (e->h2d_stream) cudaStreamDestroy(e->h2d_stream); cudaFree(e->d_counters); cudaFree(e->d_rec[0]); cudaFree(e->d_rec[1]); cudaFree(e->d_tmp);
@@ -691,6 +880,11 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
         CUE(cudaFuncSetAttribute(rt::spectro_tc256_k<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::Tc256<2>::SMEM));
     }
     for (int k = 0; k < 2; ++k) CUE(cudaMalloc(&e->d_avg[k], (size_t)e->n_streams * n * sizeof(float)));
+    {
+        const char* pp = std::getenv("RT_PROBE_PLANE");              // "0": probe the spectrogram itself (experiment)
+        if (e->reg256 && !e->tc256 && !(pp && pp[0] == '0'))
+            for (int k = 0; k < 2; ++k) CUE(cudaMalloc(&e->d_probe[k], (size_t)e->n_streams * e->n_probes * n * sizeof(float)));
+    }
     CUE(cudaMalloc(&e->d_ctr, e->n_streams * sizeof(unsigned)));
     CUE(cudaMemset(e->d_ctr, 0, e->n_streams * sizeof(unsigned)));
     CUE(cudaMalloc(&e->d_thr, e->n_streams * sizeof(float)));
@@ -711,6 +905,15 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
         const char* pr = std::getenv("RT_SCAN_PRIO");                 // experiment: "lo" = same (lowest) priority as the launch stream
         CUE(cudaStreamCreateWithPriority(&e->scan_stream, cudaStreamNonBlocking, (pr && pr[0] == 'l') ? prio_lo : prio_hi));
     }
+    if (e->scan_stream) {
+        const char* ln = std::getenv("RT_SCAN_LEAN");                 // "0": full-size scan kernels on the scan stream; "k": k lean CTAs per SM
+        int per_sm = 2;                                               // 8192 registers are left beside four 112-register spectrogram CTAs
+        if (ln) per_sm = std::atoi(ln);
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->dev) != cudaSuccess || sms < 1) sms = 148;
+        e->scan_lean = per_sm >= 1 && per_sm <= 16;
+        e->lean_ctas = sms * std::max(1, per_sm);
+    }
     CUE(cudaMallocHost(&e->h_rec, (size_t)cfg->max_records * sizeof(rt_record)));
     CUE(cudaMallocHost(&e->h_counters, 2 * sizeof(int)));
     CUE(cudaMemcpy(e->d_win, hwin.data(), n * sizeof(float), cudaMemcpyHostToDevice));
@@ -728,6 +931,11 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     } else {
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7r<true, 112>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
+        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7r<true, 112>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7r<true, 104>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
+        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7r<true, 104>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        if (const char* mr = std::getenv("RT_V7_MAXR")) e->v7_maxr = std::atoi(mr);   // 0: launch-bounds variant, 112 (default), 104
     }
 #undef CUE
     *out = e;
@@ -824,6 +1032,7 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     sa.chunk_segs = e->chunk_segs; sa.n_chunks = e->n_chunks;
     sa.win = e->d_win; sa.tw = e->d_tw; sa.S = e->d_S[next]; sa.part = e->d_part[slot];
     sa.S_stream_stride = e->s_stride;
+    sa.probe = e->d_probe[slot]; sa.probe_stride = e->cfg.probe_stride; sa.n_probes = e->n_probes;
     const bool aligned = (((uintptr_t)d_iq | stride) & 15) == 0;
     const bool use_reg = e->reg256 && aligned;
     if (e->reg256 && !aligned) return fail(RT_ERR_INVALID, "register FFT path needs 16-byte aligned IQ and stream stride");
@@ -838,7 +1047,9 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
         ta.store = 1; ta.dbg = 0; ta.prof = nullptr;
         rt::spectro_tc256_k<2><<<e->tc_grid, 512, rt::Tc256<2>::SMEM, st>>>(ta);
     } else if (use_reg) {
-        rt::spectro_reg256_v7<true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
+        if (e->v7_maxr == 112) rt::spectro_reg256_v7r<true, 112><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
+        else if (e->v7_maxr == 104) rt::spectro_reg256_v7r<true, 104><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
+        else rt::spectro_reg256_v7<true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
     } else if (e->r16 && aligned) {
         if (e->n == 4096) rt::spectro_r16_k<4096><<<grid, 256, rt::R16Cfg<4096>::SMEM, st>>>(sa);
         else rt::spectro_r16_k<1024><<<grid, 256, rt::R16Cfg<1024>::SMEM, st>>>(sa);
@@ -859,7 +1070,8 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     }
     CU(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), sc_st));
     if (evs) CU(cudaEventRecord(evs->ev[2], sc_st));
-    const bool sep_mean = !(use_reg && e->tc256) && e->n_chunks > 64;
+    const bool lean = e->scan_lean;
+    const bool sep_mean = !(use_reg && e->tc256) && (lean || e->n_chunks > 64);
     if (sep_mean) {
         row_mean_kernel<<<dim3((e->n + 127) / 128, e->n_streams), 128, 0, sc_st>>>(e->d_part[slot], e->d_avg[slot], e->n, e->n_chunks, e->T, (use_reg && !e->tc256) ? 1 : 0);
         CU(cudaGetLastError());
@@ -867,10 +1079,11 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     if (evs) CU(cudaEventRecord(evs->ev[3], sc_st));
 
     ScanArgs sc;
-    sc.S = e->d_S[next]; sc.Sprev = e->d_S[e->cur]; sc.stream_stride = e->s_stride; sc.avg = e->d_avg[slot]; sc.part = ((use_reg && e->tc256) || sep_mean) ? nullptr : e->d_part[slot]; sc.n_chunks = e->n_chunks; sc.part_perm = (use_reg && !e->tc256) ? 1 : 0; sc.thr = e->d_thr; sc.has_prev = e->d_hasprev;
+    sc.S = e->d_S[next]; sc.Sprev = e->d_S[e->cur]; sc.P = (use_reg && !e->tc256) ? e->d_probe[slot] : nullptr; sc.stream_stride = e->s_stride; sc.avg = e->d_avg[slot]; sc.part = ((use_reg && e->tc256) || sep_mean) ? nullptr : e->d_part[slot]; sc.n_chunks = e->n_chunks; sc.part_perm = (use_reg && !e->tc256) ? 1 : 0; sc.thr = e->d_thr; sc.has_prev = e->d_hasprev;
     sc.snr = (float)e->cfg.snr_threshold;
     sc.n = e->n; sc.T = e->T; sc.stride = e->cfg.probe_stride; sc.n_probes = e->n_probes;
     sc.min_cols = e->cfg.min_cols; sc.max_cols = e->cfg.max_cols;
+    sc.n_streams_scan = e->n_streams;
     sc.work = e->d_work; sc.counters = d_cnt; sc.rec = e->d_rec[slot]; sc.max_records = e->cfg.max_records;
     const int pth = e->probe_threads, eth = e->extract_threads, ect = e->extract_ctas;
     const int pbins = std::min(e->n, pth);
@@ -882,7 +1095,12 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
         else if (ppt == 16) probe_kernel<L, 16><<<pgrid, pbins, 0, sc_st>>>(sc);           \
         else probe_kernel<L, 32><<<pgrid, pbins, 0, sc_st>>>(sc);                          \
     } while (0)
-    if (use_reg && e->tc256) RT_PROBE(LAYOUT_TILE);
+    if (lean) {
+        if (use_reg && e->tc256) probe_lean_kernel<LAYOUT_TILE><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
+        else if (use_reg) probe_lean_kernel<LAYOUT_PERM><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
+        else probe_lean_kernel<LAYOUT_LINEAR><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
+    }
+    else if (use_reg && e->tc256) RT_PROBE(LAYOUT_TILE);
     else if (use_reg) RT_PROBE(LAYOUT_PERM);
     else RT_PROBE(LAYOUT_LINEAR);
 #undef RT_PROBE
@@ -895,7 +1113,12 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
         else if (emb == 12) extract_kernel<L, 12><<<ect, eth, 0, sc_st>>>(sc);             \
         else extract_kernel<L, 0><<<ect, eth, 0, sc_st>>>(sc);                             \
     } while (0)
-    if (use_reg && e->tc256) RT_EXTRACT(LAYOUT_TILE);
+    if (lean) {
+        if (use_reg && e->tc256) extract_kernel<LAYOUT_TILE, 16, 2, 2><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
+        else if (use_reg) extract_kernel<LAYOUT_PERM, 16, 2, 2><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
+        else extract_kernel<LAYOUT_LINEAR, 16, 2, 2><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
+    }
+    else if (use_reg && e->tc256) RT_EXTRACT(LAYOUT_TILE);
     else if (use_reg) RT_EXTRACT(LAYOUT_PERM);
     else RT_EXTRACT(LAYOUT_LINEAR);
 #undef RT_EXTRACT

@@ -24,6 +24,11 @@ struct SpectroArgs {
     float* S;              // generic kernel: [stream][T][n]; register kernel: [stream][T][pos(bin)] (see rt_engine.cu)
     size_t S_stream_stride;  // floats per stream
     float* part;           // [stream][chunk][n]   (FFT bin order; spectro_reg256_v7: PERM position order, like its S rows)
+    // probe plane (spectro_reg256_v7 only, optional): a dense copy of the rows the probe loop of extract_signals looks at
+    // (analyze.py:364, columns k * probe_stride), [stream][n_probes][256] in the order of the S rows, so that the probe
+    // kernel reads 1 KB rows instead of one 32-byte sector per cell
+    float* probe = nullptr;
+    int probe_stride = 1, n_probes = 0;
 };
 
 // compile-time variant selection
@@ -417,8 +422,8 @@ __device__ __forceinline__ void lane_byte_sums_alu(uint32_t addr, unsigned& sI, 
     sQ = (tQ & 0xffffu) + (tQ >> 16);
 }
 
-template <bool STORE, bool HINT = false, int MINB = 4, bool TWS = false, bool WINS = false, bool ALUSUM = false>
-__global__ void __launch_bounds__(R256v7::THREADS, MINB) spectro_reg256_v7(SpectroArgs a) {
+template <bool STORE, bool HINT, bool TWS, bool WINS, bool ALUSUM>
+__device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
     using C = R256v7;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     const int tid = threadIdx.x;
@@ -513,6 +518,8 @@ __global__ void __launch_bounds__(R256v7::THREADS, MINB) spectro_reg256_v7(Spect
     uint32_t st_off = 0, st_bar = wbar;
     unsigned phase = 0;
     int seg = first + h;
+    // probe plane: seg = pq * probe_stride + prem, kept incrementally (seg advances by SEGS_PER_ROUND per round)
+    int pq = seg / a.probe_stride, prem = seg - pq * a.probe_stride;
 
     for (int it = 0; it < n_it; ++it) {
         // uint8 -> float (0x4700bb00 is 32768 + b, no I2F), detrend (scipy detrend='constant'); window folded below
@@ -576,6 +583,15 @@ __global__ void __launch_bounds__(R256v7::THREADS, MINB) spectro_reg256_v7(Spect
                 }
             }
             sdst += C::SEGS_PER_ROUND * 256;
+            if (a.probe != nullptr) {
+                if (valid && prem == 0) {
+                    float4* dst = reinterpret_cast<float4*>(a.probe + ((size_t)s * a.n_probes + pq) * 256 + 4 * j);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) dst[16 * c] = make_float4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
+                }
+                prem += C::SEGS_PER_ROUND;
+                while (prem >= a.probe_stride) { prem -= a.probe_stride; ++pq; }
+            }
         }
         seg += C::SEGS_PER_ROUND;
         cm = cm_next;
@@ -595,6 +611,20 @@ __global__ void __launch_bounds__(R256v7::THREADS, MINB) spectro_reg256_v7(Spect
 #pragma unroll
         for (int hh = 0; hh < 2 * C::WARPS; ++hh) t += red[hh * 256 + fi];
         pd[((fi >> 6) << 6) | ((fi & 15) << 2) | ((fi >> 4) & 3)] = t;
-    }}
+    }
+}
+
+template <bool STORE, bool HINT = false, int MINB = 4, bool TWS = false, bool WINS = false, bool ALUSUM = false>
+__global__ void __launch_bounds__(R256v7::THREADS, MINB) spectro_reg256_v7(SpectroArgs a) {
+    spectro_reg256_v7_body<STORE, HINT, TWS, WINS, ALUSUM>(a);
+}
+
+// The engine's variant: registers capped at MAXR instead of "4 CTAs per SM".  At 112 registers four resident CTAs leave 8192
+// registers of an SM unused -- room for two 128-thread scan CTAs of 32 registers (rt_engine.cu, lean scan kernels), which then
+// run beside the spectrogram of the next launch instead of displacing its CTAs.
+template <bool STORE, int MAXR>
+__global__ void __maxnreg__(MAXR) spectro_reg256_v7r(SpectroArgs a) {
+    spectro_reg256_v7_body<STORE, false, false, false, false>(a);
+}
 
 }  // namespace rt
