@@ -189,19 +189,10 @@ __global__ void __launch_bounds__(NT) spectro_generic(SpectroArgs a) {
 // ---------------------------------------------------------------------------------------------
 // fixed summation order (4 interleaved partial sums over the chunks), float64: run-to-run identical and
 // identical in every CTA that evaluates it
-template <bool LEAN = false>
 __device__ __forceinline__ float row_mean_of(const float* part, int s, int fi, int n, int n_chunks, int T) {
     const float* p = part + (size_t)s * n_chunks * n + fi;
     double t[4] = {0.0, 0.0, 0.0, 0.0};
-    if (LEAN) {                                          // 32-register kernels: 8 chunk sums per round trip, same summation order
-        for (int c0 = 0; c0 < n_chunks; c0 += 8) {
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = (c0 + i < n_chunks) ? p[(size_t)(c0 + i) * n] : 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) t[i & 3] += (double)v[i];
-        }
-    } else if (n_chunks <= 48) {                                // the usual case: every chunk sum in flight at once (one round trip)
+    if (n_chunks <= 48) {                                // the usual case: every chunk sum in flight at once (one round trip)
         float v[48];
 #pragma unroll
         for (int i = 0; i < 48; ++i) v[i] = (i < n_chunks) ? p[(size_t)i * n] : 0.f;
@@ -219,13 +210,29 @@ __device__ __forceinline__ float row_mean_of(const float* part, int s, int fi, i
     return (float)(((t[0] + t[1]) + (t[2] + t[3])) / (double)T);
 }
 
-// stand-alone row means for kernels that leave many partial rows per stream (spectro_r16: one per CTA): the probe
-// kernel's prologue would repeat the long reduction in every probe group
+// stand-alone row means for kernels that leave many partial rows per stream (spectro_r16: one per CTA) and for the lean scan
+// schedule.  Four threads per bin: thread k owns the partial sum t[k] of row_mean_of (chunks k, k + 4, ...: the same values in
+// the same order), so the result is bit-identical to the one-thread version while the dependent round trips drop fourfold.
 __global__ void __launch_bounds__(128, 16) row_mean_kernel(const float* part, float* avg, int n, int n_chunks, int T, int part_perm) {
-    const int fi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int fi = g >> 2, k = g & 3;
+    const bool active = fi < n;
     // part_perm: the register kernel writes its chunk sums in PERM position order (n == 256)
     const int src = part_perm ? (((fi >> 6) << 6) | ((fi & 15) << 2) | ((fi >> 4) & 3)) : fi;
-    if (fi < n) avg[blockIdx.y * n + fi] = row_mean_of<true>(part, blockIdx.y, src, n, n_chunks, T);
+    const float* p = part + (size_t)blockIdx.y * n_chunks * n + (active ? src : 0);
+    double t = 0.0;
+    for (int c0 = k; c0 < n_chunks; c0 += 32) {          // 8 of this thread's chunk sums per memory round trip
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (c0 + 4 * i < n_chunks) ? p[(size_t)(c0 + 4 * i) * n] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += (double)v[i];
+    }
+    const double t1 = __shfl_xor_sync(0xffffffffu, t, 1);            // k even: t[k] + t[k + 1]
+    const double pair = (k & 1) ? t1 + t : t + t1;                   // always (t[even] + t[odd])
+    const double other = __shfl_xor_sync(0xffffffffu, pair, 2);
+    const double tot = (k & 2) ? other + pair : pair + other;        // (t0 + t1) + (t2 + t3)
+    if (active && k == 0) avg[blockIdx.y * n + fi] = (float)(tot / (double)T);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -664,7 +671,7 @@ struct rt_engine {
     int extract_minb = 0;                    // RT_EXTRACT_MINB: 0 (no register cap), 12 or 16 resident 128-thread CTAs per SM
     int probe_ppt = PROBE_PPT;               // probe columns per thread: 8, 16 or 32 (RT_PROBE_PPT)
     int probe_threads = 256, extract_threads = 128, extract_ctas = 148 * 24;   // scan launch shapes (RT_SCAN_SHAPE=probe,extract,ctas)
-    int v7_maxr = 112;                       // register cap of the register kernel (RT_V7_MAXR)
+    int v7_maxr = 0;                         // register cap of the register kernel (RT_V7_MAXR): 0 = launch bounds (117 registers)
     bool scan_lean = false;                  // two-stream schedule: 32-register scan CTAs that fit beside the resident spectrogram CTAs
     int lean_ctas = 148;
     float* d_win = nullptr;
@@ -881,8 +888,10 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     }
     for (int k = 0; k < 2; ++k) CUE(cudaMalloc(&e->d_avg[k], (size_t)e->n_streams * n * sizeof(float)));
     {
-        const char* pp = std::getenv("RT_PROBE_PLANE");              // "0": probe the spectrogram itself (experiment)
-        if (e->reg256 && !e->tc256 && !(pp && pp[0] == '0'))
+        // opt-in ("1"): measured 1 % slower per step than probing S itself (profiles/r01_scan_schedule_experiments.txt) --
+        // the probe kernel is bound by its dependent round trips, not by the sector traffic of its first one
+        const char* pp = std::getenv("RT_PROBE_PLANE");
+        if (e->reg256 && !e->tc256 && pp && pp[0] == '1')
             for (int k = 0; k < 2; ++k) CUE(cudaMalloc(&e->d_probe[k], (size_t)e->n_streams * e->n_probes * n * sizeof(float)));
     }
     CUE(cudaMalloc(&e->d_ctr, e->n_streams * sizeof(unsigned)));
@@ -905,14 +914,31 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
         const char* pr = std::getenv("RT_SCAN_PRIO");                 // experiment: "lo" = same (lowest) priority as the launch stream
         CUE(cudaStreamCreateWithPriority(&e->scan_stream, cudaStreamNonBlocking, (pr && pr[0] == 'l') ? prio_lo : prio_hi));
     }
-    if (e->scan_stream) {
-        const char* ln = std::getenv("RT_SCAN_LEAN");                 // "0": full-size scan kernels on the scan stream; "k": k lean CTAs per SM
-        int per_sm = 2;                                               // 8192 registers are left beside four 112-register spectrogram CTAs
+    {   // (lean kernels also run on the launch stream under RT_SCAN_OVERLAP=0: stand-alone timing of the same code)
+        // Scan kernels of the two-stream schedule: 128-thread CTAs capped at 32 registers (4096 per CTA -- what four resident
+        // spectrogram CTAs leave free on an SM), 8 per SM.  Measured 243.8 vs 255.7 us per step against the full-size scan
+        // kernels on the scan stream (profiles/r01_scan_schedule_experiments.txt).  RT_SCAN_LEAN=k: k CTAs per SM, 0: full-size.
+        const char* ln = std::getenv("RT_SCAN_LEAN");
+        int per_sm = e->scan_stream ? 8 : 0;
         if (ln) per_sm = std::atoi(ln);
         int sms = 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->dev) != cudaSuccess || sms < 1) sms = 148;
+        // default: only where it was measured to win -- the register kernel (the tensor-core kernel owns its SMs) with at least
+        // ~100 us of spectrogram per launch (short launches: the slower lean kernels become the critical path)
+        if (!ln && !(e->reg256 && !e->tc256 && (long long)e->n_streams * e->T >= 300000)) per_sm = 0;
         e->scan_lean = per_sm >= 1 && per_sm <= 16;
         e->lean_ctas = sms * std::max(1, per_sm);
+        if (e->scan_lean && !std::getenv("RT_LEAN_NO_CARVEOUT")) {
+            // same shared-memory carve-out as the resident spectrogram CTAs: an SM does not change its L1 / shared split
+            // while CTAs are resident, so a kernel asking for another split could not join them
+            CUE(cudaFuncSetAttribute(probe_lean_kernel<LAYOUT_PERM>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            CUE(cudaFuncSetAttribute(probe_lean_kernel<LAYOUT_LINEAR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            CUE(cudaFuncSetAttribute(probe_lean_kernel<LAYOUT_TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            CUE(cudaFuncSetAttribute(extract_kernel<LAYOUT_PERM, 16, 2, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            CUE(cudaFuncSetAttribute(extract_kernel<LAYOUT_LINEAR, 16, 2, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            CUE(cudaFuncSetAttribute(extract_kernel<LAYOUT_TILE, 16, 2, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            CUE(cudaFuncSetAttribute(row_mean_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        }
     }
     CUE(cudaMallocHost(&e->h_rec, (size_t)cfg->max_records * sizeof(rt_record)));
     CUE(cudaMallocHost(&e->h_counters, 2 * sizeof(int)));
@@ -931,11 +957,15 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     } else {
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7p<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
+        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7p<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7r<true, 112>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7r<true, 112>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7r<true, 104>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7r<true, 104>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        if (const char* mr = std::getenv("RT_V7_MAXR")) e->v7_maxr = std::atoi(mr);   // 0: launch-bounds variant, 112 (default), 104
+        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7r<true, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
+        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7r<true, 96>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        if (const char* mr = std::getenv("RT_V7_MAXR")) e->v7_maxr = std::atoi(mr);   // 0: launch-bounds variant (default), 112, 104, 96 (5 CTAs per SM)
     }
 #undef CUE
     *out = e;
@@ -1047,8 +1077,10 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
         ta.store = 1; ta.dbg = 0; ta.prof = nullptr;
         rt::spectro_tc256_k<2><<<e->tc_grid, 512, rt::Tc256<2>::SMEM, st>>>(ta);
     } else if (use_reg) {
-        if (e->v7_maxr == 112) rt::spectro_reg256_v7r<true, 112><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
+        if (e->d_probe[slot]) rt::spectro_reg256_v7p<true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
+        else if (e->v7_maxr == 112) rt::spectro_reg256_v7r<true, 112><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
         else if (e->v7_maxr == 104) rt::spectro_reg256_v7r<true, 104><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
+        else if (e->v7_maxr == 96) rt::spectro_reg256_v7r<true, 96><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
         else rt::spectro_reg256_v7<true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
     } else if (e->r16 && aligned) {
         if (e->n == 4096) rt::spectro_r16_k<4096><<<grid, 256, rt::R16Cfg<4096>::SMEM, st>>>(sa);
@@ -1073,7 +1105,7 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     const bool lean = e->scan_lean;
     const bool sep_mean = !(use_reg && e->tc256) && (lean || e->n_chunks > 64);
     if (sep_mean) {
-        row_mean_kernel<<<dim3((e->n + 127) / 128, e->n_streams), 128, 0, sc_st>>>(e->d_part[slot], e->d_avg[slot], e->n, e->n_chunks, e->T, (use_reg && !e->tc256) ? 1 : 0);
+        row_mean_kernel<<<dim3((4 * e->n + 127) / 128, e->n_streams), 128, 0, sc_st>>>(e->d_part[slot], e->d_avg[slot], e->n, e->n_chunks, e->T, (use_reg && !e->tc256) ? 1 : 0);
         CU(cudaGetLastError());
     }
     if (evs) CU(cudaEventRecord(evs->ev[3], sc_st));

@@ -422,7 +422,7 @@ __device__ __forceinline__ void lane_byte_sums_alu(uint32_t addr, unsigned& sI, 
     sQ = (tQ & 0xffffu) + (tQ >> 16);
 }
 
-template <bool STORE, bool HINT, bool TWS, bool WINS, bool ALUSUM>
+template <bool STORE, bool HINT, bool TWS, bool WINS, bool ALUSUM, bool PROBE = false>
 __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
     using C = R256v7;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -519,7 +519,8 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
     unsigned phase = 0;
     int seg = first + h;
     // probe plane: seg = pq * probe_stride + prem, kept incrementally (seg advances by SEGS_PER_ROUND per round)
-    int pq = seg / a.probe_stride, prem = seg - pq * a.probe_stride;
+    int pq = 0, prem = 0;
+    if (PROBE) { pq = seg / a.probe_stride; prem = seg - pq * a.probe_stride; }
 
     for (int it = 0; it < n_it; ++it) {
         // uint8 -> float (0x4700bb00 is 32768 + b, no I2F), detrend (scipy detrend='constant'); window folded below
@@ -583,7 +584,7 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
                 }
             }
             sdst += C::SEGS_PER_ROUND * 256;
-            if (a.probe != nullptr) {
+            if (PROBE) {
                 if (valid && prem == 0) {
                     float4* dst = reinterpret_cast<float4*>(a.probe + ((size_t)s * a.n_probes + pq) * 256 + 4 * j);
 #pragma unroll
@@ -625,6 +626,12 @@ __global__ void __launch_bounds__(R256v7::THREADS, MINB) spectro_reg256_v7(Spect
 template <bool STORE, int MAXR>
 __global__ void __maxnreg__(MAXR) spectro_reg256_v7r(SpectroArgs a) {
     spectro_reg256_v7_body<STORE, false, false, false, false>(a);
+}
+
+// variant that also writes the probe plane (SpectroArgs::probe)
+template <bool STORE>
+__global__ void __launch_bounds__(R256v7::THREADS, 4) spectro_reg256_v7p(SpectroArgs a) {
+    spectro_reg256_v7_body<STORE, false, false, false, false, true>(a);
 }
 
 }  // namespace rt

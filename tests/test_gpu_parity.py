@@ -247,3 +247,37 @@ def test_batched_signals_through_the_native_matcher_equal_the_oracle_matcher():
     finally:
         ba.close()
         nat.close()
+
+
+@pytest.mark.parametrize("env", [{"RT_PROBE_PLANE": "1"}, {"RT_SCAN_LEAN": "2", "RT_V7_MAXR": "112"}, {"RT_SCAN_LEAN": "1", "RT_PROBE_PLANE": "1"},
+                                 {"RT_SCAN_OVERLAP": "0"}],
+                         ids=["probe-plane", "lean-scan", "lean-scan+probe-plane", "serial"])
+@pytest.mark.parametrize("name", ["c1_default_300k", "c5_dense_300k", "c2_stream_2400k"])
+def test_optional_scan_schedules_give_the_default_records(name, env, monkeypatch):
+    """The engine's scan knobs (probe plane, lean 32-register scan kernels, register-capped spectrogram kernel, serial
+    schedule) change WHERE and WHEN the scan runs, not what it finds: same records, bit for bit, as the default."""
+    case = BY_NAME[name] if name in BY_NAME else None
+    if case is None:
+        pytest.skip("no such case")
+    g = golden_io.load(case.name)
+    kw = g.meta["analyzer"]
+    cap = case.capture()
+
+    def run():
+        ba = BatchAnalyzer(**parity.batch_kwargs(kw, fft_impl=E.FFT_AUTO))
+        out = []
+        try:
+            for b in range(len(g.blocks)):
+                ts0 = parity.block_ts(g.t0, b, kw["sdr_callback_length"], kw["sample_rate"])
+                filtered, sigs, keys = ba.process_blocks(cap[b][None, :], [ts0])[0]
+                out.append((keys, [(s.ts, s.frequency, s.duration, s.max, s.avg, s.std, s.noise, s.snr) for s in sigs]))
+        finally:
+            ba.close()
+        return out
+
+    want = run()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    got = run()
+    assert sum(len(k) for k, _ in want) > 0
+    assert got == want

@@ -13,14 +13,15 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 VARIANTS = [
-    ("overlap, v7 112 regs, lean scan 2 CTAs/SM (default)", {}),
-    ("overlap, v7 112 regs, lean scan 1 CTA/SM", {"RT_SCAN_LEAN": "1"}),
-    ("overlap, v7 104 regs, lean scan 3 CTAs/SM", {"RT_V7_MAXR": "104", "RT_SCAN_LEAN": "3"}),
-    ("overlap, v7 104 regs, lean scan 2 CTAs/SM", {"RT_V7_MAXR": "104", "RT_SCAN_LEAN": "2"}),
-    ("overlap, v7 launch bounds, full-size scan kernels (before)", {"RT_V7_MAXR": "0", "RT_SCAN_LEAN": "0"}),
-    ("serial, v7 112 regs", {"RT_SCAN_OVERLAP": "0"}),
-    ("serial, v7 104 regs", {"RT_SCAN_OVERLAP": "0", "RT_V7_MAXR": "104"}),
-    ("serial, v7 launch bounds", {"RT_SCAN_OVERLAP": "0", "RT_V7_MAXR": "0"}),
+    ("overlap, full-size scan kernels", {}),
+    ("overlap, lean scan 6 CTAs/SM", {"RT_SCAN_LEAN": "6"}),
+    ("overlap, lean scan 8 CTAs/SM", {"RT_SCAN_LEAN": "8"}),
+    ("overlap, lean scan 12 CTAs/SM", {"RT_SCAN_LEAN": "12"}),
+    ("overlap, lean scan 16 CTAs/SM", {"RT_SCAN_LEAN": "16"}),
+    ("overlap, v7 112 regs, lean scan 8 CTAs/SM", {"RT_SCAN_LEAN": "8", "RT_V7_MAXR": "112"}),
+    ("overlap, lean scan 8 CTAs/SM, probe plane", {"RT_SCAN_LEAN": "8", "RT_PROBE_PLANE": "1"}),
+    ("overlap, full-size scan kernels (again)", {}),
+    ("overlap, lean scan 8 CTAs/SM (again)", {"RT_SCAN_LEAN": "8"}),
 ]
 
 
@@ -39,7 +40,7 @@ def main():
     from pyradiotracking_b200.analyze import BatchAnalyzer
     from tools.bench_configs import run
 
-    keys = {"RT_PROBE_PLANE", "RT_SCAN_OVERLAP", "RT_SCAN_LEAN", "RT_V7_MAXR"} | {kv.split("=")[0] for kv in args.extra}
+    keys = {"RT_PROBE_PLANE", "RT_SCAN_OVERLAP", "RT_SCAN_LEAN", "RT_V7_MAXR", "RT_LEAN_NO_CARVEOUT"} | {kv.split("=")[0] for kv in args.extra}
     for name, env in VARIANTS:
         for k in keys:
             os.environ.pop(k, None)
