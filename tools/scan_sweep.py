@@ -13,15 +13,14 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 VARIANTS = [
-    ("overlap, full-size scan kernels", {}),
-    ("overlap, lean scan 6 CTAs/SM", {"RT_SCAN_LEAN": "6"}),
-    ("overlap, lean scan 8 CTAs/SM", {"RT_SCAN_LEAN": "8"}),
-    ("overlap, lean scan 12 CTAs/SM", {"RT_SCAN_LEAN": "12"}),
-    ("overlap, lean scan 16 CTAs/SM", {"RT_SCAN_LEAN": "16"}),
-    ("overlap, v7 112 regs, lean scan 8 CTAs/SM", {"RT_SCAN_LEAN": "8", "RT_V7_MAXR": "112"}),
-    ("overlap, lean scan 8 CTAs/SM, probe plane", {"RT_SCAN_LEAN": "8", "RT_PROBE_PLANE": "1"}),
-    ("overlap, full-size scan kernels (again)", {}),
-    ("overlap, lean scan 8 CTAs/SM (again)", {"RT_SCAN_LEAN": "8"}),
+    ("overlap, lean 8, chunk 256 (default)", {}),
+    ("overlap, lean 8, chunk 128", {"RT_CHUNK_SEGS": "128"}),
+    ("overlap, lean 8, chunk 64", {"RT_CHUNK_SEGS": "64"}),
+    ("overlap, lean 8, chunk 512", {"RT_CHUNK_SEGS": "512"}),
+    ("overlap, lean 8, chunk 256 (again)", {}),
+    ("overlap, lean 8, chunk 128 (again)", {"RT_CHUNK_SEGS": "128"}),
+    ("serial, chunk 128", {"RT_SCAN_OVERLAP": "0", "RT_CHUNK_SEGS": "128"}),
+    ("serial, chunk 256", {"RT_SCAN_OVERLAP": "0"}),
 ]
 
 
@@ -40,7 +39,7 @@ def main():
     from pyradiotracking_b200.analyze import BatchAnalyzer
     from tools.bench_configs import run
 
-    keys = {"RT_PROBE_PLANE", "RT_SCAN_OVERLAP", "RT_SCAN_LEAN", "RT_V7_MAXR", "RT_LEAN_NO_CARVEOUT"} | {kv.split("=")[0] for kv in args.extra}
+    keys = {"RT_PROBE_PLANE", "RT_SCAN_OVERLAP", "RT_SCAN_LEAN", "RT_V7_MAXR", "RT_LEAN_NO_CARVEOUT", "RT_CHUNK_SEGS"} | {kv.split("=")[0] for kv in args.extra}
     for name, env in VARIANTS:
         for k in keys:
             os.environ.pop(k, None)
