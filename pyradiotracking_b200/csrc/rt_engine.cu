@@ -64,7 +64,10 @@ __device__ __forceinline__ bool above(float p, float thr, float avg, float snr) 
 //                                  half-warp stores its bins as four float4, each store instruction 256 contiguous bytes
 //   TILE   (tensor-core kernel)    S[stream][t / 32][quad][t % 32][4], quad = 4 k1 + (k2 >> 2) (rt::tile_cell_off): a thread owns a
 //                                  segment, a warp stores 512 contiguous bytes, 32 time steps of a bin lie within 512 bytes
-enum { LAYOUT_LINEAR = 0, LAYOUT_PERM = 1, LAYOUT_TILE = 2 };
+//   PERM64 (register kernel, default) S[stream][t / 64][pos / 8][t % 64][pos % 8]: PERM positions, time-blocked -- a walk along time reads
+//                                  consecutive 32-byte sectors (2 KB per 64 steps) instead of one sector per 1 KB row
+enum { LAYOUT_LINEAR = 0, LAYOUT_PERM = 1, LAYOUT_TILE = 2, LAYOUT_PERM64 = 3, LAYOUT_PERM64W = 4 };   // PERM64W: blocks of 32 positions
+__host__ __device__ constexpr bool layout_is_perm(int L) { return L == LAYOUT_PERM || L == LAYOUT_PERM64 || L == LAYOUT_PERM64W; }
 
 struct CellRef {
     const float* base;     // stream base + the bin's constant part
@@ -74,12 +77,22 @@ struct CellRef {
         CellRef c;
         if (L == LAYOUT_TILE) { c.base = S + (size_t)s * stream_stride + (size_t)((fi & 15) * 4 + (fi >> 6)) * 128 + ((fi >> 4) & 3); c.step = 0; }
         else if (L == LAYOUT_PERM) { c.base = S + (size_t)s * stream_stride + (((fi >> 6) << 6) | ((fi & 15) << 2) | ((fi >> 4) & 3)); c.step = 256; }
+        else if (L == LAYOUT_PERM64) {
+            const int pos = ((fi >> 6) << 6) | ((fi & 15) << 2) | ((fi >> 4) & 3);
+            c.base = S + (size_t)s * stream_stride + (pos >> 3) * 512 + (pos & 7); c.step = 0;
+        }
+        else if (L == LAYOUT_PERM64W) {
+            const int pos = ((fi >> 6) << 6) | ((fi & 15) << 2) | ((fi >> 4) & 3);
+            c.base = S + (size_t)s * stream_stride + (pos >> 5) * 2048 + (pos & 31); c.step = 0;
+        }
         else { c.base = S + (size_t)s * stream_stride + fi; c.step = n; }
         return c;
     }
     template <int L>
     __device__ __forceinline__ float at(int t) const {
-        return L == LAYOUT_TILE ? base[(size_t)(t >> 5) * 8192 + (size_t)(t & 31) * 4] : base[(size_t)t * step];
+        return L == LAYOUT_TILE ? base[(size_t)(t >> 5) * 8192 + (size_t)(t & 31) * 4]
+             : L == LAYOUT_PERM64 ? base[((size_t)(t >> 6) << 14) + ((t & 63) << 3)]
+             : L == LAYOUT_PERM64W ? base[((size_t)(t >> 6) << 14) + ((t & 63) << 5)] : base[(size_t)t * step];
     }
 };
 
@@ -289,7 +302,7 @@ __global__ void probe_kernel(ScanArgs a) {
     // PERM layout: the thread index is the position inside the S row (and inside the chunk-sum rows, which the register
     // kernel writes in the same order), so a warp reads 128 contiguous bytes per load instead of 2 floats out of each of
     // 8 sectors; position 64 a + 4 k1 + b holds bin k1 + 16 (4 a + b)
-    auto bin_of = [](int ix) { return TILE == LAYOUT_PERM ? ((ix >> 2) & 15) + 16 * (4 * (ix >> 6) + (ix & 3)) : ix; };
+    auto bin_of = [](int ix) { return layout_is_perm(TILE) ? ((ix >> 2) & 15) + 16 * (4 * (ix >> 6) + (ix & 3)) : ix; };
     const int fi = bin_of(idx);
     const float thr = a.thr[s], snr = a.snr;
     if (tid == 0) s_n = 0;
@@ -299,7 +312,7 @@ __global__ void probe_kernel(ScanArgs a) {
     if (active) {
         // ~96 % of the probe cells fail the predicate: only a hit pays for its neighbours
         float c0[PPT];
-        if (TILE == LAYOUT_PERM && a.P != nullptr) {
+        if (layout_is_perm(TILE) && a.P != nullptr) {
             // the register kernel left a dense copy of the probe columns: a warp reads 128 contiguous bytes per load
             const float* prow = a.P + ((size_t)s * a.n_probes + (size_t)g * PPT) * 256 + idx;
 #pragma unroll
@@ -398,10 +411,10 @@ __global__ void __launch_bounds__(128, 16) probe_lean_kernel(ScanArgs a) {
         const int pb = tile % npb, g = (tile / npb) % ngr, s = tile / (npb * ngr);
         const int idx = pb * 32 + lane;
         if (idx >= a.n) continue;
-        const int fi = TILE == LAYOUT_PERM ? ((idx >> 2) & 15) + 16 * (4 * (idx >> 6) + (idx & 3)) : idx;
+        const int fi = layout_is_perm(TILE) ? ((idx >> 2) & 15) + 16 * (4 * (idx >> 6) + (idx & 3)) : idx;
         const CellRef col = CellRef::make<TILE>(a.S, a.stream_stride, s, fi, a.n);
         float c0[LEAN_PPT];
-        if (TILE == LAYOUT_PERM && a.P != nullptr) {
+        if (layout_is_perm(TILE) && a.P != nullptr) {
             const float* prow = a.P + ((size_t)s * a.n_probes + (size_t)g * LEAN_PPT) * 256 + idx;
 #pragma unroll
             for (int i = 0; i < LEAN_PPT; ++i) c0[i] = (g * LEAN_PPT + i < a.n_probes) ? prow[(size_t)i * 256] : -1.f;
@@ -662,6 +675,7 @@ struct rt_engine {
     int n = 0, T = 0, n_streams = 0, n_chunks = 0, chunk_segs = 0, n_probes = 0;
     bool reg256 = false;                     // nperseg 256: register kernel (v7) or tensor-core kernel; TILE layout
     bool tc256 = false;                      // tensor-core stage 1 (spectro_tc256.cuh)
+    int t64 = 0;                             // register kernel writes a time-blocked layout: positions per block (0 = row-major, 8, 32)
     bool r16 = false;                        // nperseg 1024 / 4096: radix-16 Stockham kernel (spectro_r16.cuh), LINEAR layout
     size_t s_stride = 0;                     // floats per stream in a spectrogram buffer
     float pscale = 1.f;                      // power factor carried by S / row means / thresholds (tensor-core path), a power of two
@@ -827,7 +841,14 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
         e->n_chunks = std::min(296, (e->T + teams - 1) / teams);
         e->chunk_segs = (e->T + e->n_chunks - 1) / e->n_chunks;      // informational
     }
-    e->s_stride = e->tc256 ? (size_t)((e->T + 31) / 32) * 8192 : (size_t)e->T * n;
+    if (const char* mr = std::getenv("RT_V7_MAXR")) e->v7_maxr = std::atoi(mr);   // 0: launch-bounds variant (default), 112, 104, 96 (5 CTAs per SM)
+    {
+        const char* ppl = std::getenv("RT_PROBE_PLANE");
+        const char* lay = std::getenv("RT_S_LAYOUT");                 // "perm": row-major S of the register kernel (before session 5)
+        const bool can = e->reg256 && !e->tc256 && !(ppl && ppl[0] == '1') && e->v7_maxr == 0;
+        e->t64 = !can || !lay ? 0 : (lay[0] == '8' ? 8 : (lay[0] == '3' ? 32 : 0));        // "8", "32"; default row-major (measured)
+    }
+    e->s_stride = e->tc256 ? (size_t)((e->T + 31) / 32) * 8192 : e->t64 ? (size_t)((e->T + 63) / 64) * 16384 : (size_t)e->T * n;
 
 #define CUE(call)                                                                                  \
     do {                                                                                           \
@@ -932,6 +953,10 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
             // same shared-memory carve-out as the resident spectrogram CTAs: an SM does not change its L1 / shared split
             // while CTAs are resident, so a kernel asking for another split could not join them
             CUE(cudaFuncSetAttribute(probe_lean_kernel<LAYOUT_PERM>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            CUE(cudaFuncSetAttribute(probe_lean_kernel<LAYOUT_PERM64>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            CUE(cudaFuncSetAttribute(extract_kernel<LAYOUT_PERM64, 16, 2, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            CUE(cudaFuncSetAttribute(probe_lean_kernel<LAYOUT_PERM64W>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            CUE(cudaFuncSetAttribute(extract_kernel<LAYOUT_PERM64W, 16, 2, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             CUE(cudaFuncSetAttribute(probe_lean_kernel<LAYOUT_LINEAR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             CUE(cudaFuncSetAttribute(probe_lean_kernel<LAYOUT_TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             CUE(cudaFuncSetAttribute(extract_kernel<LAYOUT_PERM, 16, 2, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -957,6 +982,10 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     } else {
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7t<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
+        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7t<true, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7t<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
+        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7t<true, 32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7p<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7p<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7r<true, 112>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
@@ -965,7 +994,6 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7r<true, 104>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7r<true, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7r<true, 96>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        if (const char* mr = std::getenv("RT_V7_MAXR")) e->v7_maxr = std::atoi(mr);   // 0: launch-bounds variant (default), 112, 104, 96 (5 CTAs per SM)
     }
 #undef CUE
     *out = e;
@@ -1077,7 +1105,9 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
         ta.store = 1; ta.dbg = 0; ta.prof = nullptr;
         rt::spectro_tc256_k<2><<<e->tc_grid, 512, rt::Tc256<2>::SMEM, st>>>(ta);
     } else if (use_reg) {
-        if (e->d_probe[slot]) rt::spectro_reg256_v7p<true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
+        if (e->t64 == 8) rt::spectro_reg256_v7t<true, 8><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
+        else if (e->t64 == 32) rt::spectro_reg256_v7t<true, 32><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
+        else if (e->d_probe[slot]) rt::spectro_reg256_v7p<true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
         else if (e->v7_maxr == 112) rt::spectro_reg256_v7r<true, 112><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
         else if (e->v7_maxr == 104) rt::spectro_reg256_v7r<true, 104><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
         else if (e->v7_maxr == 96) rt::spectro_reg256_v7r<true, 96><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
@@ -1112,6 +1142,9 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
 
     ScanArgs sc;
     sc.S = e->d_S[next]; sc.Sprev = e->d_S[e->cur]; sc.P = (use_reg && !e->tc256) ? e->d_probe[slot] : nullptr; sc.stream_stride = e->s_stride; sc.avg = e->d_avg[slot]; sc.part = ((use_reg && e->tc256) || sep_mean) ? nullptr : e->d_part[slot]; sc.n_chunks = e->n_chunks; sc.part_perm = (use_reg && !e->tc256) ? 1 : 0; sc.thr = e->d_thr; sc.has_prev = e->d_hasprev;
+    // timing experiment only (results are wrong): every stream's scan reads stream 0's spectrogram, i.e. a 19 MB region that stays
+    // in L2 -- the same instructions without the scattered DRAM reads (profiles/r01_scan_schedule_experiments.txt)
+    if (std::getenv("RT_SCAN_EXPERIMENT_L2")) sc.stream_stride = 0;
     sc.snr = (float)e->cfg.snr_threshold;
     sc.n = e->n; sc.T = e->T; sc.stride = e->cfg.probe_stride; sc.n_probes = e->n_probes;
     sc.min_cols = e->cfg.min_cols; sc.max_cols = e->cfg.max_cols;
@@ -1129,10 +1162,14 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     } while (0)
     if (lean) {
         if (use_reg && e->tc256) probe_lean_kernel<LAYOUT_TILE><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
+        else if (use_reg && e->t64 == 8) probe_lean_kernel<LAYOUT_PERM64><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
+        else if (use_reg && e->t64 == 32) probe_lean_kernel<LAYOUT_PERM64W><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
         else if (use_reg) probe_lean_kernel<LAYOUT_PERM><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
         else probe_lean_kernel<LAYOUT_LINEAR><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
     }
     else if (use_reg && e->tc256) RT_PROBE(LAYOUT_TILE);
+    else if (use_reg && e->t64 == 8) RT_PROBE(LAYOUT_PERM64);
+    else if (use_reg && e->t64 == 32) RT_PROBE(LAYOUT_PERM64W);
     else if (use_reg) RT_PROBE(LAYOUT_PERM);
     else RT_PROBE(LAYOUT_LINEAR);
 #undef RT_PROBE
@@ -1147,10 +1184,14 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     } while (0)
     if (lean) {
         if (use_reg && e->tc256) extract_kernel<LAYOUT_TILE, 16, 2, 2><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
+        else if (use_reg && e->t64 == 8) extract_kernel<LAYOUT_PERM64, 16, 2, 2><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
+        else if (use_reg && e->t64 == 32) extract_kernel<LAYOUT_PERM64W, 16, 2, 2><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
         else if (use_reg) extract_kernel<LAYOUT_PERM, 16, 2, 2><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
         else extract_kernel<LAYOUT_LINEAR, 16, 2, 2><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
     }
     else if (use_reg && e->tc256) RT_EXTRACT(LAYOUT_TILE);
+    else if (use_reg && e->t64 == 8) RT_EXTRACT(LAYOUT_PERM64);
+    else if (use_reg && e->t64 == 32) RT_EXTRACT(LAYOUT_PERM64W);
     else if (use_reg) RT_EXTRACT(LAYOUT_PERM);
     else RT_EXTRACT(LAYOUT_LINEAR);
 #undef RT_EXTRACT
@@ -1251,6 +1292,8 @@ int rt_engine_read_spectrogram(rt_engine* e, int32_t stream, float* out) {
     if (e->reg256) {
         if (!e->d_tmp) CU(cudaMalloc(&e->d_tmp, cells * sizeof(float)));
         if (e->tc256) untile_kernel<LAYOUT_TILE><<<(unsigned)((cells + 255) / 256), 256, 0, e->stream>>>(src, e->d_tmp, (int)cells, 1.f / e->pscale);
+        else if (e->t64 == 32) untile_kernel<LAYOUT_PERM64W><<<(unsigned)((cells + 255) / 256), 256, 0, e->stream>>>(src, e->d_tmp, (int)cells, 1.f);
+        else if (e->t64 == 8) untile_kernel<LAYOUT_PERM64><<<(unsigned)((cells + 255) / 256), 256, 0, e->stream>>>(src, e->d_tmp, (int)cells, 1.f);
         else untile_kernel<LAYOUT_PERM><<<(unsigned)((cells + 255) / 256), 256, 0, e->stream>>>(src, e->d_tmp, (int)cells, 1.f);
         CU(cudaGetLastError());
         src = e->d_tmp;

@@ -422,7 +422,10 @@ __device__ __forceinline__ void lane_byte_sums_alu(uint32_t addr, unsigned& sI, 
     sQ = (tQ & 0xffffu) + (tQ >> 16);
 }
 
-template <bool STORE, bool HINT, bool TWS, bool WINS, bool ALUSUM, bool PROBE = false>
+// T64: time-blocked S layout [t / 64][position / 8][t % 64][position % 8] instead of [t][position]: the 64 time steps of a group
+// of 8 row positions are 2 KB of contiguous memory, so the scan kernels' walks along time read consecutive sectors (whole
+// 128-byte lines, open DRAM rows) instead of one sector out of every 1 KB row.
+template <bool STORE, bool HINT, bool TWS, bool WINS, bool ALUSUM, bool PROBE = false, int T64 = 0>
 __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
     using C = R256v7;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -515,6 +518,8 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
         cm = detrend_of(my_sum);
     }
     float* sdst = a.S + (size_t)s * a.S_stream_stride + (size_t)(first + h) * 256 + 4 * j;   // += 8 * 256 floats per round
+    // T64 = positions per block (8 or 32): [t / 64][pos / T64][t % 64][pos % T64]; this thread's positions are 64 c + 4 j ...
+    float* const sbase64 = a.S + (size_t)s * a.S_stream_stride + (T64 ? ((4 * j) / (T64 ? T64 : 1)) * (64 * T64) + (4 * j) % (T64 ? T64 : 1) : 0);
     uint32_t st_off = 0, st_bar = wbar;
     unsigned phase = 0;
     int seg = first + h;
@@ -575,12 +580,12 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
         }
         if (STORE) {
             if (valid) {
-                float4* dst = reinterpret_cast<float4*>(sdst);
+                float4* dst = T64 ? reinterpret_cast<float4*>(sbase64 + ((size_t)(seg >> 6) << 14) + (seg & 63) * T64) : reinterpret_cast<float4*>(sdst);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const float4 o = make_float4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
                     if (HINT) stg128_hint(dst + 16 * c, o, pol_out);
-                    else dst[16 * c] = o;
+                    else dst[(T64 ? 1024 : 16) * c] = o;          // 64 positions further: 64 * 64 floats in either blocked layout
                 }
             }
             sdst += C::SEGS_PER_ROUND * 256;
@@ -626,6 +631,12 @@ __global__ void __launch_bounds__(R256v7::THREADS, MINB) spectro_reg256_v7(Spect
 template <bool STORE, int MAXR>
 __global__ void __maxnreg__(MAXR) spectro_reg256_v7r(SpectroArgs a) {
     spectro_reg256_v7_body<STORE, false, false, false, false>(a);
+}
+
+// time-blocked S layout (see spectro_reg256_v7_body)
+template <bool STORE, int PB>
+__global__ void __launch_bounds__(R256v7::THREADS, 4) spectro_reg256_v7t(SpectroArgs a) {
+    spectro_reg256_v7_body<STORE, false, false, false, false, false, PB>(a);
 }
 
 // variant that also writes the probe plane (SpectroArgs::probe)

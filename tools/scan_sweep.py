@@ -13,14 +13,13 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 VARIANTS = [
-    ("overlap, lean 8, chunk 256 (default)", {}),
-    ("overlap, lean 8, chunk 128", {"RT_CHUNK_SEGS": "128"}),
-    ("overlap, lean 8, chunk 64", {"RT_CHUNK_SEGS": "64"}),
-    ("overlap, lean 8, chunk 512", {"RT_CHUNK_SEGS": "512"}),
-    ("overlap, lean 8, chunk 256 (again)", {}),
-    ("overlap, lean 8, chunk 128 (again)", {"RT_CHUNK_SEGS": "128"}),
-    ("serial, chunk 128", {"RT_SCAN_OVERLAP": "0", "RT_CHUNK_SEGS": "128"}),
-    ("serial, chunk 256", {"RT_SCAN_OVERLAP": "0"}),
+    ("overlap, lean 8, row-major S (default)", {}),
+    ("overlap, lean 8, S time-blocked, 32 positions per block", {"RT_S_LAYOUT": "32"}),
+    ("overlap, lean 8, S time-blocked, 8 positions per block", {"RT_S_LAYOUT": "8"}),
+    ("serial, row-major S", {"RT_SCAN_OVERLAP": "0"}),
+    ("serial, S time-blocked, 32 positions per block", {"RT_SCAN_OVERLAP": "0", "RT_S_LAYOUT": "32"}),
+    ("overlap, lean 8, row-major S (again)", {}),
+    ("overlap, lean 8, S time-blocked 32 (again)", {"RT_S_LAYOUT": "32"}),
 ]
 
 
@@ -39,7 +38,7 @@ def main():
     from pyradiotracking_b200.analyze import BatchAnalyzer
     from tools.bench_configs import run
 
-    keys = {"RT_PROBE_PLANE", "RT_SCAN_OVERLAP", "RT_SCAN_LEAN", "RT_V7_MAXR", "RT_LEAN_NO_CARVEOUT", "RT_CHUNK_SEGS"} | {kv.split("=")[0] for kv in args.extra}
+    keys = {"RT_PROBE_PLANE", "RT_SCAN_OVERLAP", "RT_SCAN_LEAN", "RT_V7_MAXR", "RT_LEAN_NO_CARVEOUT", "RT_CHUNK_SEGS", "RT_SCAN_EXPERIMENT_L2", "RT_S_LAYOUT"} | {kv.split("=")[0] for kv in args.extra}
     for name, env in VARIANTS:
         for k in keys:
             os.environ.pop(k, None)
