@@ -87,7 +87,8 @@ typedef struct rt_record {
 
 typedef struct rt_engine rt_engine;
 
-/* Per-launch device timings accumulated while timing is enabled (milliseconds). */
+/* Per-launch device timings accumulated while timing is enabled (milliseconds).  The kernels of every 4th launch are
+ * bracketed by CUDA events (RT_TIMING_PERIOD overrides) and the sums are scaled to all `launches`. */
 typedef struct rt_timing {
     double spectrogram_ms;  /* uint8 IQ -> power cells + row sums (the dominant kernel) */
     double rowmean_ms;

@@ -441,25 +441,21 @@ __global__ void __launch_bounds__(128, 16) probe_lean_kernel(ScanArgs a) {
             const int i = __ffs(hits) - 1;
             hits &= hits - 1;
             const int ti = (g * LEAN_PPT + i) * a.stride;
-            float lo_c[PROBE_QUICK], hi_c[PROBE_QUICK];          // one round trip for the six neighbours
-#pragma unroll
-            for (int d = 1; d <= PROBE_QUICK; ++d) {
-                lo_c[d - 1] = (ti - d >= 0) ? col.at<TILE>(ti - d) : 0.f;
-                hi_c[d - 1] = (ti + d < a.T) ? col.at<TILE>(ti + d) : 0.f;
-            }
+            // neighbours by increasing distance, one round trip per distance and only on a side that is still open: ~92 % of the
+            // hits are single noise cells and are settled by the first pair (2 sectors instead of 6; this kernel runs beside
+            // the spectrogram, where DRAM sectors cost more than latency)
             bool keep = true;
             int lo = -1, hi = -1;
-#pragma unroll
-            for (int d = 1; d <= PROBE_QUICK; ++d) {
-                const int t = ti - d;
-                if (t < 0) break;
-                if (!above(lo_c[d - 1], thr, avg, snr)) { lo = t; break; }
-            }
-#pragma unroll
-            for (int d = 1; d <= PROBE_QUICK; ++d) {
-                const int t = ti + d;
-                if (t >= a.T) { keep = false; break; }
-                if (!above(hi_c[d - 1], thr, avg, snr)) { hi = t; break; }
+            bool lo_open = true, hi_open = true;
+#pragma unroll 1
+            for (int d = 1; d <= PROBE_QUICK && (lo_open || hi_open); ++d) {
+                const int tl = ti - d, th = ti + d;
+                if (lo_open && tl < 0) lo_open = false;                    // run reaches column 0: carry logic, leave it to the warp
+                if (hi_open && th >= a.T) { keep = false; break; }         // run touches the block end: dropped (analyze.py:415-417)
+                const float pl = lo_open ? col.at<TILE>(tl) : 0.f;
+                const float ph = hi_open ? col.at<TILE>(th) : 0.f;
+                if (lo_open && !above(pl, thr, avg, snr)) { lo = tl; lo_open = false; }
+                if (hi_open && !above(ph, thr, avg, snr)) { hi = th; hi_open = false; }
             }
             if (keep && lo >= 0 && hi >= 0 && hi - lo < a.min_cols) keep = false;
             if (keep && len > 0 && i == head + len) { ++len; continue; }
@@ -507,7 +503,7 @@ __global__ void __launch_bounds__(MINB > 0 ? 128 : 1024, MINB > 0 ? MINB : 1) ex
         // rarely wasted).  Backward: nearest not-above cell; if there is none and the previous probe column exists, that
         // probe already owns this run (ti_skip, analyze.py:366).
         const int lo_lim = max(ti - a.stride, 0);
-        float pb[EX_W], pf[EX_F];
+        float pb[EX_W], pf[EX_F > 0 ? EX_F : 1];          // EX_F == 0: no speculative forward fetch (fewer sectors, one more round trip)
 #pragma unroll
         for (int w = 0; w < EX_W; ++w) {
             const int t = ti - 1 - 32 * w - lane;
@@ -575,10 +571,10 @@ __global__ void __launch_bounds__(MINB > 0 ? 128 : 1024, MINB > 0 ? MINB : 1) ex
         int end = -1;
         const int span_cap = a.max_cols + 2;             // beyond this the duration test fails anyway
         bool too_long = false;
-        if (ti + 1 < T) {
+        if (EX_F > 0 && ti + 1 < T) {
             if (ti + 1 - start > span_cap) { too_long = true; skip_to = ti + 1; }
             else {
-                unsigned m[EX_F];
+                unsigned m[EX_F > 0 ? EX_F : 1];
 #pragma unroll
                 for (int w = 0; w < EX_F; ++w) m[w] = __ballot_sync(0xffffffffu, pf[w] >= 0.f && !above(pf[w], thr, avg, snr));
 #pragma unroll
@@ -688,6 +684,7 @@ struct rt_engine {
     int v7_maxr = 0;                         // register cap of the register kernel (RT_V7_MAXR): 0 = launch bounds (117 registers)
     bool scan_lean = false;                  // two-stream schedule: 32-register scan CTAs that fit beside the resident spectrogram CTAs
     int lean_ctas = 148;
+    int lean_ex = 10;                        // lean extraction windows: 10 = <1, 0> (default: fewest sectors), 20 = <2, 0>, 22 = <2, 2> (RT_LEAN_EX)
     float* d_win = nullptr;
     float2* d_tw = nullptr;
     // three spectrogram buffers: launch i writes S[i % 3] while the scan of launch i-1 still reads
@@ -728,6 +725,11 @@ struct rt_engine {
     std::vector<EvSet> ev_pool;
     size_t ev_used = 0;
     rt_timing acc{};
+    // Per-kernel events are recorded on every timing_period-th launch only: two event records between consecutive spectrogram
+    // kernels cost ~5 us of launch gap per step (232 -> 227 us at config 2).  The per-kernel sums reported by
+    // rt_engine_get_timing are scaled to all launches (sum over the timed ones x launches / timed launches).
+    int timing_period = 4;
+    int64_t timed_launches = 0, timing_launches = 0;      // launches with events / launches while timing was on
 };
 
 namespace {
@@ -947,6 +949,7 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
         // default: only where it was measured to win -- the register kernel (the tensor-core kernel owns its SMs) with at least
         // ~100 us of spectrogram per launch (short launches: the slower lean kernels become the critical path)
         if (!ln && !(e->reg256 && !e->tc256 && (long long)e->n_streams * e->T >= 300000)) per_sm = 0;
+        if (const char* lx = std::getenv("RT_LEAN_EX")) { const int v = std::atoi(lx); if (v == 10 || v == 20 || v == 22) e->lean_ex = v; }
         e->scan_lean = per_sm >= 1 && per_sm <= 16;
         e->lean_ctas = sms * std::max(1, per_sm);
         if (e->scan_lean && !std::getenv("RT_LEAN_NO_CARVEOUT")) {
@@ -1071,7 +1074,9 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     if (e->launch_seq >= RT_SLOTS && e->scan_stream) CU(cudaStreamWaitEvent(st, e->done[slot], 0));
 
     rt_engine::EvSet* evs = nullptr;
-    if (e->timing) {
+    if (e->timing) e->timing_launches++;
+    if (e->timing && ((e->timing_launches - 1) % e->timing_period) == 0) {
+        e->timed_launches++;
         if (e->ev_used == e->ev_pool.size()) {
             if (e->ev_pool.size() >= 4096) { int rc = harvest_timing(e); if (rc) return rc; }
             else {
@@ -1183,11 +1188,18 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
         else extract_kernel<L, 0><<<ect, eth, 0, sc_st>>>(sc);                             \
     } while (0)
     if (lean) {
-        if (use_reg && e->tc256) extract_kernel<LAYOUT_TILE, 16, 2, 2><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
-        else if (use_reg && e->t64 == 8) extract_kernel<LAYOUT_PERM64, 16, 2, 2><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
-        else if (use_reg && e->t64 == 32) extract_kernel<LAYOUT_PERM64W, 16, 2, 2><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
-        else if (use_reg) extract_kernel<LAYOUT_PERM, 16, 2, 2><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
-        else extract_kernel<LAYOUT_LINEAR, 16, 2, 2><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
+#define RT_LEAN_EXTRACT(L)                                                                                          \
+    do {                                                                                                            \
+        if (e->lean_ex == 10) extract_kernel<L, 16, 1, 0><<<e->lean_ctas, 128, 0, sc_st>>>(sc);                     \
+        else if (e->lean_ex == 20) extract_kernel<L, 16, 2, 0><<<e->lean_ctas, 128, 0, sc_st>>>(sc);                \
+        else extract_kernel<L, 16, 2, 2><<<e->lean_ctas, 128, 0, sc_st>>>(sc);                                      \
+    } while (0)
+        if (use_reg && e->tc256) RT_LEAN_EXTRACT(LAYOUT_TILE);
+        else if (use_reg && e->t64 == 8) RT_LEAN_EXTRACT(LAYOUT_PERM64);
+        else if (use_reg && e->t64 == 32) RT_LEAN_EXTRACT(LAYOUT_PERM64W);
+        else if (use_reg) RT_LEAN_EXTRACT(LAYOUT_PERM);
+        else RT_LEAN_EXTRACT(LAYOUT_LINEAR);
+#undef RT_LEAN_EXTRACT
     }
     else if (use_reg && e->tc256) RT_EXTRACT(LAYOUT_TILE);
     else if (use_reg && e->t64 == 8) RT_EXTRACT(LAYOUT_PERM64);
@@ -1318,6 +1330,7 @@ int rt_engine_enable_timing(rt_engine* e, int32_t on) {
     if (!e) return fail(RT_ERR_INVALID, "null engine");
     if (!on) { int rc = harvest_timing(e); if (rc) return rc; }
     e->timing = on != 0;
+    if (const char* tp = std::getenv("RT_TIMING_PERIOD")) { const int v = std::atoi(tp); if (v >= 1) e->timing_period = v; }
     return RT_OK;
 }
 
@@ -1327,7 +1340,11 @@ int rt_engine_get_timing(rt_engine* e, rt_timing* out, int32_t reset) {
     int rc = harvest_timing(e);
     if (rc) return rc;
     *out = e->acc;
-    if (reset) e->acc = rt_timing{};
+    if (e->timed_launches > 0 && e->timed_launches != e->timing_launches) {
+        const double k = (double)e->timing_launches / (double)e->timed_launches;
+        out->spectrogram_ms *= k; out->rowmean_ms *= k; out->probe_ms *= k; out->extract_ms *= k;
+    }
+    if (reset) { e->acc = rt_timing{}; e->timed_launches = 0; e->timing_launches = 0; }
     return RT_OK;
 }
 
