@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "../../include/rt_engine.h"
+#include "predicate.h"
 #include "spectro256.cuh"
 #include "spectro_tc256.cuh"
 #include "spectro_r16.cuh"
@@ -53,10 +54,9 @@ int fail(int code, const std::string& msg) {
 // device helpers
 // ---------------------------------------------------------------------------------------------
 
-// analyze.py:370-379: a cell is part of a run unless it undershoots either threshold.
-__device__ __forceinline__ bool above(float p, float thr, float avg, float snr) {
-    return !(p < thr) && !(__fdiv_rn(p, avg) < snr);
-}
+// analyze.py:370-379: a cell is part of a run unless it undershoots either threshold (predicate.h)
+using rt::Pred;
+__device__ __forceinline__ bool above(float p, float thr, float avg, float snr) { return rt::above_exact(p, thr, avg, snr); }
 
 // Spectrogram layouts.
 //   LINEAR (generic kernel)        S[stream][t][bin]
@@ -426,9 +426,10 @@ __global__ void __launch_bounds__(128, 16) probe_lean_kernel(ScanArgs a) {
             }
         }
         const float thr = a.thr[s], avg = a.avg[s * a.n + fi];
+        const Pred pred(thr, avg, snr);
         unsigned hits = 0;
 #pragma unroll
-        for (int i = 0; i < LEAN_PPT; ++i) hits |= (c0[i] >= 0.f && above(c0[i], thr, avg, snr)) ? (1u << i) : 0u;
+        for (int i = 0; i < LEAN_PPT; ++i) hits |= (c0[i] >= 0.f && pred(c0[i])) ? (1u << i) : 0u;
         int head = -1, len = 0;              // open chain (LEAN_PPT == PROBE_CHAIN: a chain never leaves the tile)
         auto flush = [&]() {
             if (len > 0) {
@@ -454,8 +455,8 @@ __global__ void __launch_bounds__(128, 16) probe_lean_kernel(ScanArgs a) {
                 if (hi_open && th >= a.T) { keep = false; break; }         // run touches the block end: dropped (analyze.py:415-417)
                 const float pl = lo_open ? col.at<TILE>(tl) : 0.f;
                 const float ph = hi_open ? col.at<TILE>(th) : 0.f;
-                if (lo_open && !above(pl, thr, avg, snr)) { lo = tl; lo_open = false; }
-                if (hi_open && !above(ph, thr, avg, snr)) { hi = th; hi_open = false; }
+                if (lo_open && !pred(pl)) { lo = tl; lo_open = false; }
+                if (hi_open && !pred(ph)) { hi = th; hi_open = false; }
             }
             if (keep && lo >= 0 && hi >= 0 && hi - lo < a.min_cols) keep = false;
             if (keep && len > 0 && i == head + len) { ++len; continue; }
@@ -493,6 +494,7 @@ __global__ void __launch_bounds__(MINB > 0 ? 128 : 1024, MINB > 0 ? MINB : 1) ex
         const CellRef col = CellRef::make<TILE>(a.S, a.stream_stride, s, fi, n);
         const CellRef pcol = CellRef::make<TILE>(a.Sprev, a.stream_stride, s, fi, n);
         const float thr = a.thr[s], avg = a.avg[s * n + fi], snr = a.snr;
+        const Pred pred(thr, avg, snr);
         int skip_to = 0;                                 // every cell in [previous member's probe, skip_to) is known to be above
       for (int mem = 0; mem < members; ++mem) {
         const int ti = ti0 + mem * a.stride;
@@ -518,7 +520,7 @@ __global__ void __launch_bounds__(MINB > 0 ? 128 : 1024, MINB > 0 ? MINB : 1) ex
         {
             unsigned m[EX_W];
 #pragma unroll
-            for (int w = 0; w < EX_W; ++w) m[w] = __ballot_sync(0xffffffffu, pb[w] >= 0.f && !above(pb[w], thr, avg, snr));
+            for (int w = 0; w < EX_W; ++w) m[w] = __ballot_sync(0xffffffffu, pb[w] >= 0.f && !pred(pb[w]));
 #pragma unroll
             for (int w = 0; w < EX_W; ++w)
                 if (nb < 0 && m[w]) nb = ti - 1 - 32 * w - (__ffs(m[w]) - 1);
@@ -530,7 +532,7 @@ __global__ void __launch_bounds__(MINB > 0 ? 128 : 1024, MINB > 0 ? MINB : 1) ex
                 const int t = base - 32 * w - lane;
                 const bool valid = t >= lo_lim;
                 const float p = valid ? col.at<TILE>(t) : 0.f;
-                m[w] = __ballot_sync(0xffffffffu, valid && !above(p, thr, avg, snr));
+                m[w] = __ballot_sync(0xffffffffu, valid && !pred(p));
             }
 #pragma unroll
             for (int w = 0; w < EX_W; ++w)
@@ -556,7 +558,7 @@ __global__ void __launch_bounds__(MINB > 0 ? 128 : 1024, MINB > 0 ? MINB : 1) ex
                     const int jj = base + 32 * w + lane;
                     const bool valid = jj <= jcap;
                     const float p = valid ? pcol.at<TILE>(T - jj) : 0.f;
-                    m[w] = __ballot_sync(0xffffffffu, valid && !above(p, thr, avg, snr));
+                    m[w] = __ballot_sync(0xffffffffu, valid && !pred(p));
                 }
 #pragma unroll
                 for (int w = 0; w < EX_W; ++w)
@@ -576,7 +578,7 @@ __global__ void __launch_bounds__(MINB > 0 ? 128 : 1024, MINB > 0 ? MINB : 1) ex
             else {
                 unsigned m[EX_F > 0 ? EX_F : 1];
 #pragma unroll
-                for (int w = 0; w < EX_F; ++w) m[w] = __ballot_sync(0xffffffffu, pf[w] >= 0.f && !above(pf[w], thr, avg, snr));
+                for (int w = 0; w < EX_F; ++w) m[w] = __ballot_sync(0xffffffffu, pf[w] >= 0.f && !pred(pf[w]));
 #pragma unroll
                 for (int w = 0; w < EX_F; ++w)
                     if (end < 0 && m[w]) end = ti + 1 + 32 * w + (__ffs(m[w]) - 1);
@@ -590,7 +592,7 @@ __global__ void __launch_bounds__(MINB > 0 ? 128 : 1024, MINB > 0 ? MINB : 1) ex
                 const int t = base + 32 * w + lane;
                 const bool valid = t < T;
                 const float p = valid ? col.at<TILE>(t) : 0.f;
-                m[w] = __ballot_sync(0xffffffffu, valid && !above(p, thr, avg, snr));
+                m[w] = __ballot_sync(0xffffffffu, valid && !pred(p));
             }
 #pragma unroll
             for (int w = 0; w < EX_W; ++w)
@@ -620,7 +622,10 @@ __global__ void __launch_bounds__(MINB > 0 ? 128 : 1024, MINB > 0 ? MINB : 1) ex
                 if (pv[w] >= 0.f) {
                     mx = fmaxf(mx, pv[w]);
                     sum += (double)pv[w];
-                    const double db = 10.0 * log10((double)pv[w]);
+                    // dB of one cell in float (MUFU.LG2: ~1e-6 dB absolute error, the record tolerance is 5e-4 dB); the sums stay
+                    // float64.  A float64 log10 costs ~100 instructions per cell -- a third of this kernel, which shares its
+                    // issue slots with the spectrogram of the next launch.
+                    const double db = (double)(3.0102999566398120f * __log2f(pv[w]));
                     sdb += db;
                     sdb2 += db * db;
                 }

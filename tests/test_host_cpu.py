@@ -233,3 +233,12 @@ def test_radix16_stockham_index_algebra_on_cpu(N):
         for q in range(256):
             out[q + 256 * np.arange(4)] = F4 @ Y[q + 256 * np.arange(4)]
     assert np.max(np.abs(out - np.fft.fft(x))) < 1e-9 * N
+
+
+def test_cheap_predicate_equals_exact_predicate_on_cpu(tmp_path):
+    """csrc/predicate.h: the 3-instruction predicate of the scan kernels takes the decision of the exact one
+    (analyze.py:370-379) for every float, also within a few ulp of the thresholds and for degenerate row means."""
+    exe = tmp_path / "pred_host_check"
+    subprocess.run(["g++", "-O2", "-o", str(exe), os.path.join(ROOT, "tests", "pred_host_check.cpp")], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) > 10_000_000 and int(out[1]) == 0

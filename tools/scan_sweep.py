@@ -13,19 +13,12 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 VARIANTS = [
-    ("overlap, lean scan 8 CTAs/SM, windows <1,0> (default)", {}),
-    ("overlap, lean scan 8 CTAs/SM, windows <2,2>", {"RT_LEAN_EX": "22"}),
-    ("overlap, lean scan 1 CTA/SM", {"RT_SCAN_LEAN": "1"}),
-    ("overlap, full-size scan kernels", {"RT_SCAN_LEAN": "0"}),
-    ("overlap, lean scan, v7 112 registers", {"RT_V7_MAXR": "112"}),
-    ("overlap, lean scan, probe plane", {"RT_PROBE_PLANE": "1"}),
-    ("overlap, lean scan, S time-blocked 8", {"RT_S_LAYOUT": "8"}),
-    ("overlap, lean scan, S time-blocked 32", {"RT_S_LAYOUT": "32"}),
-    ("overlap, lean scan, chunk 256", {"RT_CHUNK_SEGS": "256"}),
+    ("overlap, lean scan (default)", {}),
+    ("overlap, lean scan 12 CTAs/SM", {"RT_SCAN_LEAN": "12"}),
     ("overlap, lean scan, scan reads an L2-resident S (timing experiment, wrong results)", {"RT_SCAN_EXPERIMENT_L2": "1"}),
-    ("overlap, lean scan, per-kernel events on every launch", {"RT_TIMING_PERIOD": "1"}),
     ("overlap, lean scan, no per-kernel events", {"RT_BENCH_NO_KERNEL_TIMING": "1"}),
     ("serial", {"RT_SCAN_OVERLAP": "0"}),
+    ("overlap, lean scan (default, again)", {}),
 ]
 
 
