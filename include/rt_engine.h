@@ -124,15 +124,18 @@ int rt_engine_reset_stream(rt_engine *e, int32_t stream);
 int rt_engine_process(rt_engine *e, const uint8_t *iq, int32_t iq_on_device, size_t stream_stride_bytes,
                       rt_record *out, int32_t max_out, int32_t *n_out);
 
-/* The same in two halves: enqueue only (asynchronous; a host `iq` must stay valid until the fetch) ... */
+/* The same in two halves: enqueue only (asynchronous; `iq` -- host or device -- must stay valid and unchanged until the
+ * fetch or an rt_engine_join: the kernels run on engine-internal streams that are ordered AFTER the work already queued on
+ * the launch stream, but work queued on the launch stream later is not ordered after them) ... */
 int rt_engine_launch(rt_engine *e, const uint8_t *iq, int32_t iq_on_device, size_t stream_stride_bytes);
 /* ... then wait for the OLDEST unfetched launch, copy back and sort its records.  Two launches may be in
  * flight (launch i+1 can be queued before fetch i); a third launch drops the oldest unfetched result. */
 int rt_engine_fetch(rt_engine *e, rt_record *out, int32_t max_out, int32_t *n_out);
 
 /*
- * The scan kernels (row mean, probe, extraction) of a launch run on an engine-internal stream so that they
- * overlap the spectrogram of the NEXT launch.  rt_engine_join makes the launch stream (the engine's own or the
+ * The spectrogram kernels of consecutive launches alternate between two engine-internal streams and the scan kernels (row
+ * mean, probe, extraction) run on a third, so that launch i+1 overlaps the tail and the scan of launch i.
+ * rt_engine_join makes the launch stream (the engine's own or the
  * one given to rt_engine_set_stream) wait for everything launched so far, e.g. before the caller records an
  * event on it or reuses a device-resident `iq` buffer from another stream.  rt_engine_fetch does not need it.
  */

@@ -699,6 +699,12 @@ struct rt_engine {
     float* d_part[2] = {nullptr, nullptr};   // chunk row sums, by launch parity
     float* d_probe[2] = {nullptr, nullptr};  // probe plane (register kernel), by launch parity
     cudaStream_t scan_stream = nullptr;      // row mean / probe / extract: overlaps the next launch's spectrogram
+    // Consecutive spectrogram kernels alternate between two internal streams (forked from the launch stream by an event), so
+    // that launch i+1 fills the SMs while the last CTAs of launch i drain: step 227.7 -> 213.9 us at config 2
+    // (RT_LAUNCH_STREAMS=1: spectrogram kernels on the launch stream itself)
+    cudaStream_t lstream[2] = {nullptr, nullptr};
+    cudaEvent_t fork_ev = nullptr;
+    int n_lstreams = 1;
     cudaEvent_t spec_done[2] = {nullptr, nullptr};
     float* d_avg[2] = {nullptr, nullptr};    // row means, by launch parity (written by the spectrogram kernel)
     unsigned* d_ctr = nullptr;               // [n_streams] finished-CTA tickets of the spectrogram kernel
@@ -773,6 +779,8 @@ void free_engine(rt_engine* e) {
     for (auto& ev : e->spec_done) if (ev) cudaEventDestroy(ev);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->scan_stream) cudaStreamDestroy(e->scan_stream);
+    for (auto& ls : e->lstream) if (ls) cudaStreamDestroy(ls);
+    if (e->fork_ev) cudaEventDestroy(e->fork_ev);
     if (e->h_rec) cudaFreeHost(e->h_rec);
     if (e->h_counters) cudaFreeHost(e->h_counters);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
@@ -942,6 +950,14 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
         const char* pr = std::getenv("RT_SCAN_PRIO");                 // experiment: "lo" = same (lowest) priority as the launch stream
         CUE(cudaStreamCreateWithPriority(&e->scan_stream, cudaStreamNonBlocking, (pr && pr[0] == 'l') ? prio_lo : prio_hi));
     }
+    if (e->scan_stream) {
+        const char* ls = std::getenv("RT_LAUNCH_STREAMS");
+        if (!(ls && ls[0] == '1')) {
+            for (auto& q : e->lstream) CUE(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+            CUE(cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming));
+            e->n_lstreams = 2;
+        }
+    }
     {   // (lean kernels also run on the launch stream under RT_SCAN_OVERLAP=0: stand-alone timing of the same code)
         // Scan kernels of the two-stream schedule: 128-thread CTAs capped at 32 registers (4096 per CTA -- what four resident
         // spectrogram CTAs leave free on an SM), 8 per SM.  Measured 243.8 vs 255.7 us per step against the full-size scan
@@ -1044,6 +1060,11 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     if (stream_stride_bytes < block_bytes && e->n_streams > 1) return fail(RT_ERR_INVALID, "stream_stride_bytes smaller than one block");
     CU(cudaSetDevice(e->dev));
     cudaStream_t st = e->stream;
+    if (e->n_lstreams == 2) {
+        CU(cudaEventRecord(e->fork_ev, e->stream));
+        st = e->lstream[e->launch_seq & 1];
+        CU(cudaStreamWaitEvent(st, e->fork_ev, 0));
+    }
 
     const uint8_t* d_iq = iq;
     size_t stride = stream_stride_bytes;

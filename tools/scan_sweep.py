@@ -13,12 +13,16 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 VARIANTS = [
-    ("overlap, lean scan (default)", {}),
+    ("overlap, lean scan 8 CTAs/SM, two launch streams (default)", {}),
+    ("overlap, lean scan, one launch stream", {"RT_LAUNCH_STREAMS": "1"}),
     ("overlap, lean scan 12 CTAs/SM", {"RT_SCAN_LEAN": "12"}),
+    ("overlap, lean scan 4 CTAs/SM", {"RT_SCAN_LEAN": "4"}),
+    ("overlap, full-size scan kernels", {"RT_SCAN_LEAN": "0"}),
+    ("overlap, lean scan, chunk 256", {"RT_CHUNK_SEGS": "256"}),
+    ("overlap, lean scan, chunk 64", {"RT_CHUNK_SEGS": "64"}),
     ("overlap, lean scan, scan reads an L2-resident S (timing experiment, wrong results)", {"RT_SCAN_EXPERIMENT_L2": "1"}),
-    ("overlap, lean scan, no per-kernel events", {"RT_BENCH_NO_KERNEL_TIMING": "1"}),
     ("serial", {"RT_SCAN_OVERLAP": "0"}),
-    ("overlap, lean scan (default, again)", {}),
+    ("overlap, lean scan 8 CTAs/SM, two launch streams (default, again)", {}),
 ]
 
 
@@ -37,7 +41,7 @@ def main():
     from pyradiotracking_b200.analyze import BatchAnalyzer
     from tools.bench_configs import run
 
-    keys = {"RT_PROBE_PLANE", "RT_SCAN_OVERLAP", "RT_SCAN_LEAN", "RT_V7_MAXR", "RT_LEAN_NO_CARVEOUT", "RT_CHUNK_SEGS", "RT_SCAN_EXPERIMENT_L2", "RT_S_LAYOUT", "RT_LEAN_EX", "RT_BENCH_NO_KERNEL_TIMING", "RT_TIMING_PERIOD"} | {kv.split("=")[0] for kv in args.extra}
+    keys = {"RT_PROBE_PLANE", "RT_SCAN_OVERLAP", "RT_SCAN_LEAN", "RT_V7_MAXR", "RT_LEAN_NO_CARVEOUT", "RT_CHUNK_SEGS", "RT_SCAN_EXPERIMENT_L2", "RT_S_LAYOUT", "RT_LEAN_EX", "RT_BENCH_NO_KERNEL_TIMING", "RT_TIMING_PERIOD", "RT_LAUNCH_STREAMS"} | {kv.split("=")[0] for kv in args.extra}
     for name, env in VARIANTS:
         for k in keys:
             os.environ.pop(k, None)
