@@ -686,7 +686,7 @@ struct rt_engine {
     int extract_minb = 0;                    // RT_EXTRACT_MINB: 0 (no register cap), 12 or 16 resident 128-thread CTAs per SM
     int probe_ppt = PROBE_PPT;               // probe columns per thread: 8, 16 or 32 (RT_PROBE_PPT)
     int probe_threads = 256, extract_threads = 128, extract_ctas = 148 * 24;   // scan launch shapes (RT_SCAN_SHAPE=probe,extract,ctas)
-    int v7_maxr = 0;                         // register cap of the register kernel (RT_V7_MAXR): 0 = launch bounds (117 registers)
+    int v7_maxr = -1;                        // RT_V7_MAXR: -1 = launch bounds + pinned addresses (default), 0 = launch bounds, 112 / 104 / 96 = register cap
     bool scan_lean = false;                  // two-stream schedule: 32-register scan CTAs that fit beside the resident spectrogram CTAs
     int lean_ctas = 148;
     int lean_ex = 10;                        // lean extraction windows: 10 = <1, 0> (default: fewest sectors), 20 = <2, 0>, 22 = <2, 2> (RT_LEAN_EX)
@@ -860,7 +860,7 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     {
         const char* ppl = std::getenv("RT_PROBE_PLANE");
         const char* lay = std::getenv("RT_S_LAYOUT");                 // "perm": row-major S of the register kernel (before session 5)
-        const bool can = e->reg256 && !e->tc256 && !(ppl && ppl[0] == '1') && e->v7_maxr == 0;
+        const bool can = e->reg256 && !e->tc256 && !(ppl && ppl[0] == '1') && e->v7_maxr <= 0;
         e->t64 = !can || !lay ? 0 : (lay[0] == '8' ? 8 : (lay[0] == '3' ? 32 : 0));        // "8", "32"; default row-major (measured)
     }
     e->s_stride = e->tc256 ? (size_t)((e->T + 31) / 32) * 8192 : e->t64 ? (size_t)((e->T + 63) / 64) * 16384 : (size_t)e->T * n;
@@ -1010,6 +1010,8 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7t<true, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7t<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7t<true, 32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7n<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
+        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7n<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7p<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7p<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7r<true, 112>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
@@ -1142,6 +1144,7 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
         else if (e->v7_maxr == 112) rt::spectro_reg256_v7r<true, 112><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
         else if (e->v7_maxr == 104) rt::spectro_reg256_v7r<true, 104><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
         else if (e->v7_maxr == 96) rt::spectro_reg256_v7r<true, 96><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
+        else if (e->v7_maxr == -1) rt::spectro_reg256_v7n<true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);   // RT_V7_MAXR=-1: pinned addresses
         else rt::spectro_reg256_v7<true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
     } else if (e->r16 && aligned) {
         if (e->n == 4096) rt::spectro_r16_k<4096><<<grid, 256, rt::R16Cfg<4096>::SMEM, st>>>(sa);

@@ -425,7 +425,7 @@ __device__ __forceinline__ void lane_byte_sums_alu(uint32_t addr, unsigned& sI, 
 // T64: time-blocked S layout [t / 64][position / 8][t % 64][position % 8] instead of [t][position]: the 64 time steps of a group
 // of 8 row positions are 2 KB of contiguous memory, so the scan kernels' walks along time read consecutive sectors (whole
 // 128-byte lines, open DRAM rows) instead of one sector out of every 1 KB row.
-template <bool STORE, bool HINT, bool TWS, bool WINS, bool ALUSUM, bool PROBE = false, int T64 = 0>
+template <bool STORE, bool HINT, bool TWS, bool WINS, bool ALUSUM, bool PROBE = false, int T64 = 0, bool PIN = false>
 __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
     using C = R256v7;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -444,8 +444,16 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
     const uint32_t xt = sm0 + C::RAW_BYTES + (tid >> 4) * (C::XTILE * 4);
     const uint32_t my_u16 = wraw + h * C::RAW_STRIDE + 2 * j;        // + stage offset + 32*n1
     const uint32_t my_sum = wraw + h * C::RAW_STRIDE + 16 * j;       // + stage offset (+256)
-    const uint32_t xt_st = xt + 8 * j;                                // + k1 * XROW * 4
-    const uint32_t xt_ld = xt + j * (C::XROW * 4);                    // + 16 * c
+    uint32_t xt_st = xt + 8 * j;                                      // + k1 * XROW * 4
+    uint32_t xt_ld = xt + j * (C::XROW * 4);                          // + 16 * c
+    uint32_t my_u16_ = my_u16, my_sum_ = my_sum;
+    if (PIN) {
+        // opaque to the compiler: without this ptxas re-derives these four addresses from SR_TID.X in every round
+        // (S2R -> SHF -> IMAD -> IADD3 in front of the round's first LDS)
+        asm volatile("" : "+r"(my_u16_), "+r"(my_sum_), "+r"(xt_st), "+r"(xt_ld));
+    }
+    int h16 = 16 * h;                                                 // shift of this half-warp's field in the REDUX sums
+    if (PIN) asm volatile("" : "+r"(h16));
     // global source of the segment pair of round `it`: base + (first + 8*it) * 512
     const uint8_t* gsrc = a.iq + (size_t)s * a.stream_stride + (size_t)first * 512;
     const int last_seg = seg1 - 1;
@@ -506,16 +514,16 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
         if (ALUSUM) lane_byte_sums_alu(addr, sI, sQ);
         else lane_byte_sums(addr, sI, sQ);
         // warp-wide REDUX: half-warp 0 in the low 16 bits, half-warp 1 in the high 16 (each total < 2^16)
-        const unsigned tI = __reduce_add_sync(0xffffffffu, sI << (16 * h));
-        const unsigned tQ = __reduce_add_sync(0xffffffffu, sQ << (16 * h));
-        const unsigned mI = (tI >> (16 * h)) & 0xffffu, mQ = (tQ >> (16 * h)) & 0xffffu;
+        const unsigned tI = __reduce_add_sync(0xffffffffu, sI << h16);
+        const unsigned tQ = __reduce_add_sync(0xffffffffu, sQ << h16);
+        const unsigned mI = (tI >> h16) & 0xffffu, mQ = (tQ >> h16) & 0xffffu;
         return c_scale(c_make(__uint_as_float(0x4B000000u | mI), __uint_as_float(0x4B000000u | mQ)), 0.00390625f);
     };
 
     cpk cm = c_make(0.f, 0.f);
     if (n_it > 0) {
         mbar_wait(wbar, 0);
-        cm = detrend_of(my_sum);
+        cm = detrend_of(my_sum_);
     }
     float* sdst = a.S + (size_t)s * a.S_stream_stride + (size_t)(first + h) * 256 + 4 * j;   // += 8 * 256 floats per round
     // T64 = positions per block (8 or 32): [t / 64][pos / T64][t % 64][pos % T64]; this thread's positions are 64 c + 4 j ...
@@ -532,7 +540,7 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
         cpk v[16];
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) {
-            const unsigned u = lds_u16(my_u16 + st_off + 32 * n1);
+            const unsigned u = lds_u16(my_u16_ + st_off + 32 * n1);
             const cpk f = c_make(__uint_as_float(__byte_perm(u, 0x47000000u, 0x7604)),
                                  __uint_as_float(__byte_perm(u, 0x47000000u, 0x7614)));
             v[n1] = c_sub(f, cm);
@@ -548,7 +556,7 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
         cpk cm_next = cm;
         if (it + 1 < n_it) {
             mbar_wait(st_bar, phase);
-            cm_next = detrend_of(my_sum + st_off);
+            cm_next = detrend_of(my_sum_ + st_off);
         }
 
         if (WINS) {
@@ -631,6 +639,12 @@ __global__ void __launch_bounds__(R256v7::THREADS, MINB) spectro_reg256_v7(Spect
 template <bool STORE, int MAXR>
 __global__ void __maxnreg__(MAXR) spectro_reg256_v7r(SpectroArgs a) {
     spectro_reg256_v7_body<STORE, false, false, false, false>(a);
+}
+
+// addresses pinned in registers (see PIN in spectro_reg256_v7_body)
+template <bool STORE>
+__global__ void __launch_bounds__(R256v7::THREADS, 4) spectro_reg256_v7n(SpectroArgs a) {
+    spectro_reg256_v7_body<STORE, false, false, false, false, false, 0, true>(a);
 }
 
 // time-blocked S layout (see spectro_reg256_v7_body)

@@ -250,8 +250,8 @@ def test_batched_signals_through_the_native_matcher_equal_the_oracle_matcher():
 
 
 @pytest.mark.parametrize("env", [{"RT_PROBE_PLANE": "1"}, {"RT_SCAN_LEAN": "2", "RT_V7_MAXR": "112"}, {"RT_SCAN_LEAN": "1", "RT_PROBE_PLANE": "1"},
-                                 {"RT_SCAN_OVERLAP": "0"}, {"RT_S_LAYOUT": "8"}, {"RT_S_LAYOUT": "32", "RT_SCAN_LEAN": "2"}, {"RT_LAUNCH_STREAMS": "2"}],
-                         ids=["probe-plane", "lean-scan", "lean-scan+probe-plane", "serial", "time-blocked-8", "time-blocked-32", "two-launch-streams"])
+                                 {"RT_SCAN_OVERLAP": "0"}, {"RT_S_LAYOUT": "8"}, {"RT_S_LAYOUT": "32", "RT_SCAN_LEAN": "2"}, {"RT_LAUNCH_STREAMS": "1"}, {"RT_V7_MAXR": "-1"}],
+                         ids=["probe-plane", "lean-scan", "lean-scan+probe-plane", "serial", "time-blocked-8", "time-blocked-32", "one-launch-stream", "pinned-addresses"])
 @pytest.mark.parametrize("name", ["c1_default_300k", "c5_dense_300k", "c2_stream_2400k"])
 def test_optional_scan_schedules_give_the_default_records(name, env, monkeypatch):
     """The engine's scan knobs (probe plane, lean 32-register scan kernels, register-capped spectrogram kernel, serial

@@ -13,16 +13,14 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 VARIANTS = [
-    ("overlap, lean scan 8 CTAs/SM, two launch streams (default)", {}),
-    ("overlap, lean scan, one launch stream", {"RT_LAUNCH_STREAMS": "1"}),
-    ("overlap, lean scan 12 CTAs/SM", {"RT_SCAN_LEAN": "12"}),
-    ("overlap, lean scan 4 CTAs/SM", {"RT_SCAN_LEAN": "4"}),
-    ("overlap, full-size scan kernels", {"RT_SCAN_LEAN": "0"}),
-    ("overlap, lean scan, chunk 256", {"RT_CHUNK_SEGS": "256"}),
-    ("overlap, lean scan, chunk 64", {"RT_CHUNK_SEGS": "64"}),
-    ("overlap, lean scan, scan reads an L2-resident S (timing experiment, wrong results)", {"RT_SCAN_EXPERIMENT_L2": "1"}),
-    ("serial", {"RT_SCAN_OVERLAP": "0"}),
-    ("overlap, lean scan 8 CTAs/SM, two launch streams (default, again)", {}),
+    ("default", {}),
+    ("v7 with pinned addresses", {"RT_V7_MAXR": "-1"}),
+    ("serial, default", {"RT_SCAN_OVERLAP": "0"}),
+    ("serial, v7 with pinned addresses", {"RT_SCAN_OVERLAP": "0", "RT_V7_MAXR": "-1"}),
+    ("default (again)", {}),
+    ("v7 with pinned addresses (again)", {"RT_V7_MAXR": "-1"}),
+    ("serial, default (again)", {"RT_SCAN_OVERLAP": "0"}),
+    ("serial, v7 with pinned addresses (again)", {"RT_SCAN_OVERLAP": "0", "RT_V7_MAXR": "-1"}),
 ]
 
 
