@@ -530,6 +530,8 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
     float* const sbase64 = a.S + (size_t)s * a.S_stream_stride + (T64 ? ((4 * j) / (T64 ? T64 : 1)) * (64 * T64) + (4 * j) % (T64 ? T64 : 1) : 0);
     uint32_t st_off = 0, st_bar = wbar;
     unsigned phase = 0;
+    const uint8_t* g_next = gsrc + (size_t)C::STAGES * (C::SEGS_PER_ROUND * 512);   // source of the next round to be issued
+    int sg_next = first + C::STAGES * C::SEGS_PER_ROUND;
     int seg = first + h;
     // probe plane: seg = pq * probe_stride + prem, kept incrementally (seg advances by SEGS_PER_ROUND per round)
     int pq = 0, prem = 0;
@@ -548,8 +550,18 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
         // this stage's bytes are in registers: refill it with the segments STAGES rounds ahead
         __syncwarp();
         if (it + C::STAGES < n_it) {
-            if (elect_one()) issue(it + C::STAGES, it % C::STAGES);
+            if (PIN) {
+                // running source pointer / ring slot instead of re-deriving both from the round number (uniform datapath)
+                if (elect_one()) {
+                    const uint8_t* p1 = (sg_next + 1 <= last_seg) ? g_next + 512 : g_next;
+                    mbar_expect_tx_a(st_bar, 1024);
+                    bulk_g2s_a(wraw + st_off, g_next, 512, st_bar);
+                    bulk_g2s_a(wraw + st_off + C::RAW_STRIDE, p1, 512, st_bar);
+                }
+            } else if (elect_one()) issue(it + C::STAGES, it % C::STAGES);
         }
+        g_next += C::SEGS_PER_ROUND * 512;
+        sg_next += C::SEGS_PER_ROUND;
         // advance to the next stage; its byte sums overlap the butterflies below
         st_off += C::STAGE_BYTES; st_bar += 8;
         if (st_off == C::STAGES * C::STAGE_BYTES) { st_off = 0; st_bar = wbar; phase ^= 1; }

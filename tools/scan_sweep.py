@@ -13,14 +13,12 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 VARIANTS = [
-    ("default", {}),
-    ("v7 with pinned addresses", {"RT_V7_MAXR": "-1"}),
+    ("default (pinned addresses + running TMA pointer)", {}),
     ("serial, default", {"RT_SCAN_OVERLAP": "0"}),
-    ("serial, v7 with pinned addresses", {"RT_SCAN_OVERLAP": "0", "RT_V7_MAXR": "-1"}),
+    ("unpinned v7", {"RT_V7_MAXR": "0"}),
+    ("serial, unpinned v7", {"RT_SCAN_OVERLAP": "0", "RT_V7_MAXR": "0"}),
     ("default (again)", {}),
-    ("v7 with pinned addresses (again)", {"RT_V7_MAXR": "-1"}),
     ("serial, default (again)", {"RT_SCAN_OVERLAP": "0"}),
-    ("serial, v7 with pinned addresses (again)", {"RT_SCAN_OVERLAP": "0", "RT_V7_MAXR": "-1"}),
 ]
 
 
