@@ -425,7 +425,7 @@ __device__ __forceinline__ void lane_byte_sums_alu(uint32_t addr, unsigned& sI, 
 // T64: time-blocked S layout [t / 64][position / 8][t % 64][position % 8] instead of [t][position]: the 64 time steps of a group
 // of 8 row positions are 2 KB of contiguous memory, so the scan kernels' walks along time read consecutive sectors (whole
 // 128-byte lines, open DRAM rows) instead of one sector out of every 1 KB row.
-template <bool STORE, bool HINT, bool TWS, bool WINS, bool ALUSUM, bool PROBE = false, int T64 = 0, bool PIN = false>
+template <bool STORE, bool HINT, bool TWS, bool WINS, bool ALUSUM, bool PROBE = false, int T64 = 0, bool PIN = false, bool PACC = false>
 __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
     using C = R256v7;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -488,6 +488,9 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
     // per-thread constants: window at samples 16*n1 + j, inter-pass twiddles W256^{j*k1}
     // (in registers, or -- TWS / WINS -- in a shared-memory table to buy a fifth / sixth resident CTA)
     float wj[16], twr[16], twi[16], acc[16];
+    cpk acc2[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc2[c] = c_make(0.f, 0.f);
     const uint32_t tab_tw = sm0 + C::TAB_OFF + 8 * j, tab_win = sm0 + C::TAB_OFF + 2048 + 4 * j;
     if (TWS || WINS) {
         float2* ttw = reinterpret_cast<float2*>(dyn_smem + C::TAB_OFF);
@@ -596,7 +599,11 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
         for (int k2 = 0; k2 < 16; ++k2) {
             const float re = c_re(v[k2]), im = c_im(v[k2]);
             p[k2] = fmaf(im, im, re * re);
-            acc[k2] = fmaf(p[k2], m, acc[k2]);
+            if (!PACC) acc[k2] = fmaf(p[k2], m, acc[k2]);
+        }
+        if (PACC) {                                 // row sums as 8 packed FMAs instead of 16 scalar ones (same lanes, half the issue slots)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc2[c] = c_fma_s(c_make(p[2 * c], p[2 * c + 1]), m, acc2[c]);
         }
         if (STORE) {
             if (valid) {
@@ -628,7 +635,7 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
     float* red = reinterpret_cast<float*>(dyn_smem);
     const int hw = tid >> 4;
 #pragma unroll
-    for (int k2 = 0; k2 < 16; ++k2) red[hw * 256 + 16 * k2 + j] = acc[k2];
+    for (int k2 = 0; k2 < 16; ++k2) red[hw * 256 + 16 * k2 + j] = PACC ? ((k2 & 1) ? c_im(acc2[k2 >> 1]) : c_re(acc2[k2 >> 1])) : acc[k2];
     __syncthreads();
     // written in the order of the S rows (PERM position, see rt_engine.cu) so that the probe kernel reads both coalesced
     float* pd = a.part + ((size_t)s * a.n_chunks + blockIdx.x) * 256;
@@ -657,6 +664,12 @@ __global__ void __maxnreg__(MAXR) spectro_reg256_v7r(SpectroArgs a) {
 template <bool STORE>
 __global__ void __launch_bounds__(R256v7::THREADS, 4) spectro_reg256_v7n(SpectroArgs a) {
     spectro_reg256_v7_body<STORE, false, false, false, false, false, 0, true>(a);
+}
+
+// experiment variants of v7n: byte sums on the ALU pipe and / or packed row-sum accumulators
+template <bool STORE, bool ALUSUM, bool PACC>
+__global__ void __launch_bounds__(R256v7::THREADS, 4) spectro_reg256_v7x(SpectroArgs a) {
+    spectro_reg256_v7_body<STORE, false, false, false, ALUSUM, false, 0, true, PACC>(a);
 }
 
 // time-blocked S layout (see spectro_reg256_v7_body)

@@ -13,12 +13,21 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 VARIANTS = [
-    ("default (pinned addresses + running TMA pointer)", {}),
-    ("serial, default", {"RT_SCAN_OVERLAP": "0"}),
+    ("default: v7n, lean scan 8 CTAs/SM <1,0>, two launch streams", {}),
+    ("one launch stream", {"RT_LAUNCH_STREAMS": "1"}),
+    ("lean extraction windows <2,2>", {"RT_LEAN_EX": "22"}),
+    ("lean scan 1 CTA/SM", {"RT_SCAN_LEAN": "1"}),
+    ("full-size scan kernels", {"RT_SCAN_LEAN": "0"}),
     ("unpinned v7", {"RT_V7_MAXR": "0"}),
-    ("serial, unpinned v7", {"RT_SCAN_OVERLAP": "0", "RT_V7_MAXR": "0"}),
-    ("default (again)", {}),
-    ("serial, default (again)", {"RT_SCAN_OVERLAP": "0"}),
+    ("v7 112 registers", {"RT_V7_MAXR": "112"}),
+    ("v7n + ALU byte sums + packed row sums", {"RT_V7_MAXR": "-4"}),
+    ("probe plane", {"RT_PROBE_PLANE": "1"}),
+    ("S time-blocked 8", {"RT_S_LAYOUT": "8"}),
+    ("S time-blocked 32", {"RT_S_LAYOUT": "32"}),
+    ("chunk 256", {"RT_CHUNK_SEGS": "256"}),
+    ("scan reads an L2-resident S (timing experiment, wrong results)", {"RT_SCAN_EXPERIMENT_L2": "1"}),
+    ("per-kernel events on every launch", {"RT_TIMING_PERIOD": "1"}),
+    ("serial", {"RT_SCAN_OVERLAP": "0"}),
 ]
 
 
