@@ -844,6 +844,15 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     }
     if (const char* cs = std::getenv("RT_CHUNK_SEGS")) { const int v = std::atoi(cs); if (e->reg256 && v >= 8 && v % 8 == 0) e->chunk_segs = v; }
     if (const char* mb = std::getenv("RT_EXTRACT_MINB")) { const int v = std::atoi(mb); if (v == 0 || v == 12 || v == 16) e->extract_minb = v; }
+    {
+        // small launches (a single wideband stream): fewer probe columns per thread = more CTAs; 32 columns per thread would
+        // leave a 20 MS/s nperseg-1024 block with 16 probe CTAs, each a long chain of dependent round trips
+        const long long bin_blocks = (n + 255) / 256;
+        for (int ppt = 32; ppt >= 8; ppt >>= 1) {
+            e->probe_ppt = ppt;
+            if (bin_blocks * ((e->n_probes + ppt - 1) / ppt) * e->n_streams >= 2 * 148) break;
+        }
+    }
     if (const char* pp = std::getenv("RT_PROBE_PPT")) { const int v = std::atoi(pp); if (v == 8 || v == 16 || v == 32) e->probe_ppt = v; }
     if (const char* sh = std::getenv("RT_SCAN_SHAPE")) {
         int a = 0, b = 0, c = 0;
