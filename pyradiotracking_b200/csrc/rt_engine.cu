@@ -840,7 +840,7 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     if (e->reg256) {
         // short blocks (300 kS/s SDRs, replay): shorter chunks = more CTAs per stream.  The choice depends on T only, so a
         // stream gives bit-identical row means whether it runs alone or inside a batch.
-        e->chunk_segs = e->T >= 2048 ? 128 : 64;       // 128 vs 256 at T = 9375: 8 waves of CTAs instead of 4, step 243.2 -> 240.5 us
+        e->chunk_segs = e->T >= 8192 ? 192 : (e->T >= 2048 ? 128 : 64);   // 192 at T = 9375 (49 chunks per stream): step 205.0 -> 202.8 us vs 128, 209.8 at 256
     }
     if (const char* cs = std::getenv("RT_CHUNK_SEGS")) { const int v = std::atoi(cs); if (e->reg256 && v >= 8 && v % 8 == 0) e->chunk_segs = v; }
     if (const char* mb = std::getenv("RT_EXTRACT_MINB")) { const int v = std::atoi(mb); if (v == 0 || v == 12 || v == 16) e->extract_minb = v; }
@@ -969,10 +969,10 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     }
     {   // (lean kernels also run on the launch stream under RT_SCAN_OVERLAP=0: stand-alone timing of the same code)
         // Scan kernels of the two-stream schedule: 128-thread CTAs capped at 32 registers (4096 per CTA -- what four resident
-        // spectrogram CTAs leave free on an SM), 8 per SM.  Measured 243.8 vs 255.7 us per step against the full-size scan
+        // spectrogram CTAs leave free on an SM), 12 per SM (8 ... 16 time the same within 1 %).  Measured 243.8 vs 255.7 us per step against the full-size scan
         // kernels on the scan stream (profiles/r01_scan_schedule_experiments.txt).  RT_SCAN_LEAN=k: k CTAs per SM, 0: full-size.
         const char* ln = std::getenv("RT_SCAN_LEAN");
-        int per_sm = e->scan_stream ? 8 : 0;
+        int per_sm = e->scan_stream ? 12 : 0;
         if (ln) per_sm = std::atoi(ln);
         int sms = 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->dev) != cudaSuccess || sms < 1) sms = 148;
