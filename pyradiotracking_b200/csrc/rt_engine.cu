@@ -1366,6 +1366,7 @@ int rt_engine_read_row_means(rt_engine* e, int32_t stream, float* out) {
     if (!e || !out || stream < 0 || stream >= e->n_streams) return fail(RT_ERR_INVALID, "bad argument");
     if (!e->launched) return fail(RT_ERR_STATE, "no launch yet");
     CU(cudaSetDevice(e->dev));
+    if (e->scan_stream) CU(cudaStreamSynchronize(e->scan_stream));      // the row means are written on the scan stream
     CU(cudaMemcpyAsync(out, e->d_avg[(int)((e->launch_seq - 1) % RT_SLOTS)] + (size_t)stream * e->n, e->n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     if (e->pscale != 1.f)

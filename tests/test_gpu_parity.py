@@ -281,3 +281,35 @@ def test_optional_scan_schedules_give_the_default_records(name, env, monkeypatch
     got = run()
     assert sum(len(k) for k, _ in want) > 0
     assert got == want
+
+
+@pytest.mark.parametrize("thr_dbw,snr_db,min_ms,max_ms", [(-95.0, 3.0, 4.0, 20.0), (-88.0, 8.0, 8.0, 40.0), (-92.0, 0.5, 2.0, 60.0),
+                                                          (-90.0, 5.0, 15.0, 25.0), (-97.0, 2.0, 1.0, 10.0)])
+@pytest.mark.parametrize("name", ["c1_default_300k", "c5_dense_300k"])
+def test_detection_parameters_sweep_against_the_oracle(name, thr_dbw, snr_db, min_ms, max_ms):
+    """Other thresholds / duration limits than the fixtures were generated with: other probe strides (1 ... 17 columns), chain
+    lengths and duration gates through the same kernels; the oracle (pinned by the fixtures) is the checker."""
+    case = BY_NAME[name]
+    g = golden_io.load(case.name)
+    kw = dict(g.meta["analyzer"])
+    kw.update(signal_threshold_dbw=thr_dbw, snr_threshold_db=snr_db, signal_min_duration_ms=min_ms, signal_max_duration_ms=max_ms)
+    cap = case.capture()
+    P = parity.oracle_params(kw)
+    ora = R.OracleAnalyzer(P)
+    ba = BatchAnalyzer(**parity.batch_kwargs(kw, max_records=1 << 18))
+    try:
+        last = None
+        totals = dict(oracle=0, gpu=0, near_threshold_mismatch=0)
+        for b in range(min(4, len(g.blocks))):
+            ts0 = parity.block_ts(g.t0, b, kw["sdr_callback_length"], kw["sample_rate"])
+            freqs, times, S, found, kept = ora.process_block(cap[b], ts0)
+            filtered, sigs, keys = ba.process_blocks(cap[b][None, :], [ts0])[0]
+            stats = parity.compare_block(P, S, last, found, sigs, keys)
+            for k in totals:
+                totals[k] += stats[k]
+            if stats["near_threshold_mismatch"] == 0:
+                assert [(s.ts, s.frequency) for s in filtered] == [(d.ts, d.frequency) for d in kept]
+            last = S
+        assert totals["near_threshold_mismatch"] <= max(2, totals["oracle"] // 50)
+    finally:
+        ba.close()
