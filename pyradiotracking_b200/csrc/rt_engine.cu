@@ -1185,7 +1185,7 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     CU(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), sc_st));
     if (evs) CU(cudaEventRecord(evs->ev[2], sc_st));
     const bool lean = e->scan_lean;
-    const bool sep_mean = !(use_reg && e->tc256) && (lean || e->n_chunks > 64);
+    const bool sep_mean = !(use_reg && e->tc256) && (lean || e->n_chunks > 48);
     if (sep_mean) {
         row_mean_kernel<<<dim3((4 * e->n + 127) / 128, e->n_streams), 128, 0, sc_st>>>(e->d_part[slot], e->d_avg[slot], e->n, e->n_chunks, e->T, (use_reg && !e->tc256) ? 1 : 0);
         CU(cudaGetLastError());

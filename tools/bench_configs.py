@@ -77,6 +77,7 @@ def main():
 
     a = (args.steps, args.warmup, torch, synth, BatchAnalyzer)
     run("configs[0] single 300 kS/s stream", synth.C1, 1, *a)
+    run("one 2.4 MS/s stream (a single live SDR at the RTL-SDR maximum)", synth.C2, 1, *a)
     run("configs[1] 64 x 2.4 MS/s (register kernel)", synth.C2, 64, *a)
     run("configs[1] 64 x 2.4 MS/s (tensor-core kernel)", synth.C2, 64, *a, fft_impl=E.FFT_TC256)
     run("configs[2] 20 MS/s nperseg 1024", synth.C3A, 1, *a)
