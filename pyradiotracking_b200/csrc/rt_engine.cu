@@ -1025,6 +1025,8 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7x<true, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7x<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7x<true, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7h<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
+        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7h<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7n<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7n<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7p<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
@@ -1159,6 +1161,7 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
         else if (e->v7_maxr == 112) rt::spectro_reg256_v7r<true, 112><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
         else if (e->v7_maxr == 104) rt::spectro_reg256_v7r<true, 104><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
         else if (e->v7_maxr == 96) rt::spectro_reg256_v7r<true, 96><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
+        else if (e->v7_maxr == -5) rt::spectro_reg256_v7h<true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
         else if (e->v7_maxr == -2) rt::spectro_reg256_v7x<true, true, false><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
         else if (e->v7_maxr == -3) rt::spectro_reg256_v7x<true, false, true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
         else if (e->v7_maxr == -4) rt::spectro_reg256_v7x<true, true, true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);

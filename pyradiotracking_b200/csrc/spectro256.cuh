@@ -459,7 +459,7 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
     const int last_seg = seg1 - 1;
 
     uint64_t pol_in = 0, pol_out = 0;
-    if (HINT) { pol_in = policy_evict_first(); pol_out = policy_evict_last(); }
+    if (HINT) { pol_in = policy_evict_first(); pol_out = PIN ? policy_evict_first() : policy_evict_last(); }   // v7h (HINT + PIN): S stores evict-first (streaming)
     auto issue = [&](int itx, int st) {                              // executed by one elected lane
         const int sg = first + C::SEGS_PER_ROUND * itx;
         const uint8_t* p0 = gsrc + (size_t)itx * (C::SEGS_PER_ROUND * 512);
@@ -670,6 +670,12 @@ __global__ void __launch_bounds__(R256v7::THREADS, 4) spectro_reg256_v7n(Spectro
 template <bool STORE, bool ALUSUM, bool PACC>
 __global__ void __launch_bounds__(R256v7::THREADS, 4) spectro_reg256_v7x(SpectroArgs a) {
     spectro_reg256_v7_body<STORE, false, false, false, ALUSUM, false, 0, true, PACC>(a);
+}
+
+// experiment variant of v7n: L2 hints (IQ evict-first, S evict-last) under the overlapped schedule
+template <bool STORE>
+__global__ void __launch_bounds__(R256v7::THREADS, 4) spectro_reg256_v7h(SpectroArgs a) {
+    spectro_reg256_v7_body<STORE, true, false, false, false, false, 0, true, false>(a);
 }
 
 // time-blocked S layout (see spectro_reg256_v7_body)
