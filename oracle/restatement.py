@@ -92,12 +92,23 @@ def spectrogram(x: np.ndarray, fs: float, window, nperseg: int) -> Tuple[np.ndar
     win = resolve_window(window, nperseg)
     T = N // nperseg if N >= nperseg else 0
     seg = x[: T * nperseg].reshape(T, nperseg)
-    seg = seg - np.mean(seg, axis=-1, keepdims=True)        # detrend='constant'
-    seg = win.astype(np.complex128) * seg                   # window
-    X = np.fft.fft(seg, n=nperseg, axis=-1)                 # two-sided
+    # scipy keeps the transforms time-major (its Sxx is a transposed view whose per-bin rows are 16*nperseg-byte gathers);
+    # the values are the same whichever way they are stored, so they are written bin-major here (pocketfft copies every
+    # 1-D transform in and out anyway) and extract_* walk contiguous rows.  Blocks of segments / of bins keep the
+    # intermediate arrays cache-resident; every segment sees exactly scipy's operations in scipy's order.
+    XT = np.empty((nperseg, T), dtype=np.complex128)
+    for a in range(0, T, 512):
+        blk = seg[a:a + 512]
+        d = blk - np.mean(blk, axis=-1, keepdims=True)     # detrend='constant'
+        d *= win                                            # window (real x complex, same products as scipy's win * d)
+        np.fft.fft(d, n=nperseg, axis=-1, out=XT[:, a:a + 512].T)   # two-sided
     scale = 1.0 / (fs * (win * win).sum())                  # density scaling
-    P = (np.conjugate(X) * X) * scale
-    S = P.real.T                                            # (nperseg, T), time-major storage like scipy's
+    S = np.empty((nperseg, T))
+    for r in range(0, nperseg, 8):
+        Y = XT[r:r + 8]
+        np.multiply(np.conjugate(Y), Y, out=Y)              # scipy: conj(result) * result, then *= scale, then .real
+        Y *= scale
+        S[r:r + 8] = Y.real
     freqs = np.fft.fftfreq(nperseg, 1 / fs)
     times = np.arange(nperseg / 2, N - nperseg / 2 + 1, nperseg) / float(fs)
     return freqs, times, S
@@ -151,13 +162,14 @@ def _above(p, avg, P: Params) -> bool:
     return True
 
 
-def _finish(P: Params, freqs, times, S, last, fi, start, end, avg, ts_start) -> Optional[Detection]:
+def _finish(P: Params, freqs, times, S, last, fi, start, end, avg, ts_start, row=None) -> Optional[Detection]:
     """Duration test and per-signal statistics (analyze.py:419-450)."""
     start_dt = -times[-start] if start < 0 else times[start]
     duration_s = times[end] - start_dt
     if duration_s < P.signal_min_duration or duration_s > P.signal_max_duration:
         return None
-    row = S[fi]
+    if row is None:
+        row = S[fi]
     data = np.concatenate((last[fi][start:], row[:end])) if start < 0 else row[start:end]
     mean = np.mean(data)
     ts = (ts_start + datetime.timedelta(seconds=start_dt)).astimezone(UTC)
@@ -207,33 +219,41 @@ def extract_sequential(P: Params, freqs, times, S, last, ts_start) -> List[Detec
 def extract_runs(P: Params, freqs, times, S, last, ts_start) -> List[Detection]:
     """Same result as `extract_sequential`, computed per maximal run (SURVEY.md §8a,
     "parallel formulation"): every maximal run of above-cells is evaluated at most once,
-    iff a probe column k*stride lies inside it and it does not touch the block end."""
+    iff a probe column k*stride lies inside it and it does not touch the block end.
+
+    Rows with a probe hit are handled as one bin-major block; the row mean is taken lazily, only for rows where a probed cell reaches
+    the absolute threshold, like analyze.py:370-375."""
     out: List[Detection] = []
     T = len(times)
     if T == 0:
         return out
     stride = max(1, int(P.signal_min_duration / (times[1] - times[0])))
     reach = 0 if last is None else -len(last[0]) + 1
-    probe_hit = S[:, ::stride] >= P.signal_threshold
-    for fi in np.nonzero(probe_hit.any(axis=1))[0]:
-        row = S[fi]
-        avg = np.mean(row)
-        with np.errstate(divide="ignore", invalid="ignore"):
-            ab = ~(row < P.signal_threshold) & ~(row / avg < P.snr_threshold)
-        edge = np.diff(np.concatenate(([0], ab.view(np.int8), [0])))
-        run_s = np.nonzero(edge == 1)[0]
-        run_e = np.nonzero(edge == -1)[0]
-        seen = (-(-run_s // stride) * stride < run_e) & (run_e != T)
-        for s, e in zip(run_s[seen].tolist(), run_e[seen].tolist()):
-            if s > 0:
-                start = s - 1           # the not-above cell before the run is part of the window
-            else:
-                start = 0               # analyze.py:382-398 from column 0 (which is above)
-                while start > reach and _above(last[fi, start] if start < 0 else row[0], avg, P):
-                    start -= 1
-            det = _finish(P, freqs, times, S, last, int(fi), start, e, avg, ts_start)
-            if det is not None:
-                out.append(det)
+    rows = np.nonzero((S[:, ::stride] >= P.signal_threshold).any(axis=1))[0]
+    if len(rows) == 0:
+        return out
+    Sc = S if (len(rows) == S.shape[0] and S.flags.c_contiguous) else np.ascontiguousarray(S[rows])   # bin-major candidate rows
+    avgs = Sc.mean(axis=1)                                  # bit-identical to np.mean(S[fi]) (pairwise sums of the same values)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ab = ~(Sc < P.signal_threshold) & ~(Sc / avgs[:, None] < P.snr_threshold)
+    pad = np.zeros((len(rows), T + 2), dtype=np.int8)
+    pad[:, 1:-1] = ab
+    edge = pad[:, 1:] != pad[:, :-1]                        # first cell of a run / one past its last, alternating along a row
+    er, ec = np.nonzero(edge)                               # sorted by (row, then time)
+    rs, run_s, run_e = er[0::2], ec[0::2], ec[1::2]
+    seen = (-(-run_s // stride) * stride < run_e) & (run_e != T)
+    for r, s, e in zip(rs[seen].tolist(), run_s[seen].tolist(), run_e[seen].tolist()):
+        fi = int(rows[r])
+        avg = avgs[r]
+        if s > 0:
+            start = s - 1               # the not-above cell before the run is part of the window
+        else:
+            start = 0                   # analyze.py:382-398 from column 0 (which is above)
+            while start > reach and _above(last[fi, start] if start < 0 else Sc[r, 0], avg, P):
+                start -= 1
+        det = _finish(P, freqs, times, S, last, fi, start, e, avg, ts_start, row=Sc[r])
+        if det is not None:
+            out.append(det)
     return out
 
 
