@@ -25,13 +25,14 @@
 extern "C" {
 #endif
 
-#define RT_ABI_VERSION 1
+#define RT_ABI_VERSION 2
 
 enum {
     RT_OK = 0,
     RT_ERR_INVALID = -1,      /* bad argument / unsupported configuration */
     RT_ERR_CUDA = -2,         /* CUDA runtime error, no device, wrong architecture */
-    RT_ERR_OVERFLOW = -3,     /* more candidate records than max_records; none are lost silently */
+    RT_ERR_OVERFLOW = -3,     /* more candidate records than max_records (or than the caller's buffer): the first ones are
+                                 still returned and *n_out says how many there were; none are lost silently */
     RT_ERR_STATE = -4         /* call order violated (fetch without launch, ...) */
 };
 
@@ -41,6 +42,14 @@ enum {
     RT_FFT_GENERIC = 1,   /* shared-memory Stockham FFT, any power-of-two nperseg */
     RT_FFT_REG256 = 2,    /* nperseg 256: 16x16 FFT in registers (packed fp32x2), TMA-fed */
     RT_FFT_TC256 = 3      /* nperseg 256, boxcar/hann/hamming: first FFT stage on the tensor cores (tcgen05, fp16 x split-fp16 -> fp32) */
+};
+
+/* scan_schedule: where the scan kernels (row mean, probe, extraction) of a launch run. */
+enum {
+    RT_SCAN_AUTO = 0,     /* RT_SCAN_LEAN for nperseg 256 launches of >= 300 k segments, otherwise RT_SCAN_OVERLAP */
+    RT_SCAN_SERIAL = 1,   /* on the launch stream, after the spectrogram (no overlap with the next launch) */
+    RT_SCAN_OVERLAP = 2,  /* full-size scan kernels on an engine-internal high-priority stream */
+    RT_SCAN_LEAN = 3      /* 32-register scan kernels that fit BESIDE the resident spectrogram CTAs of the next launch */
 };
 
 /*
@@ -62,9 +71,18 @@ typedef struct rt_config {
     int32_t probe_stride;       /* max(1, int(signal_min_duration / (times[1]-times[0]))), float64 on the host (analyze.py:354,364) */
     int32_t min_cols;           /* coarse duration gate in spectrogram columns; the exact float64 test */
     int32_t max_cols;           /*   (analyze.py:419-433) is applied by the host on the returned records */
-    int32_t max_records;        /* capacity of one call's record list */
+    int32_t max_records;        /* capacity of one call's record list; 0 = sized for the worst case (one record per probe
+                                   column of every bin, capped at 4 Mi records), so that a noisy band cannot overflow it */
     int32_t fft_impl;           /* RT_FFT_* */
-    int32_t reserved;
+    int32_t scan_schedule;      /* RT_SCAN_* */
+    int32_t launch_streams;     /* 0 = auto; 1 = spectrogram kernels on the launch stream itself; 2 = consecutive launches
+                                   alternate between two internal streams (launch i+1 fills the SMs while launch i drains) */
+    int32_t chunk_segs;         /* nperseg 256: segments per CTA, a multiple of 8; 0 = auto (64 / 128 / 192 by block length) */
+    int32_t blocks_per_launch;  /* offline replay: this many CONSECUTIVE callback blocks of every stream per launch (>= 1).
+                                   Block b of stream s is the analyzer unit s * blocks_per_launch + b: it has its own row
+                                   means and records, and its carry (analyze.py:383-398) is block b-1 of the same launch,
+                                   or the last block of the previous launch for b = 0 */
+    int32_t reserved[3];        /* zero */
 } rt_config;
 
 /*
@@ -75,7 +93,7 @@ typedef struct rt_config {
  * The host turns records into Signal objects (analyze.py:419-450).
  */
 typedef struct rt_record {
-    int32_t stream;     /* analyzer index in the batch */
+    int32_t stream;     /* analyzer unit: stream index * blocks_per_launch + block index within the launch */
     int32_t fi;         /* frequency bin, FFT order (no fftshift) */
     int32_t start;      /* first column of the statistics window (inclusive) */
     int32_t end;        /* last column + 1 */
@@ -87,8 +105,8 @@ typedef struct rt_record {
 
 typedef struct rt_engine rt_engine;
 
-/* Per-launch device timings accumulated while timing is enabled (milliseconds).  The kernels of every 4th launch are
- * bracketed by CUDA events (RT_TIMING_PERIOD overrides) and the sums are scaled to all `launches`. */
+/* Per-launch device timings accumulated while timing is enabled (milliseconds).  The kernels of every `period`-th launch
+ * (rt_engine_enable_timing) are bracketed by CUDA events and the sums are scaled to all `launches`. */
 typedef struct rt_timing {
     double spectrogram_ms;  /* uint8 IQ -> power cells + row sums (the dominant kernel) */
     double rowmean_ms;
@@ -115,11 +133,12 @@ int rt_engine_reset_stream(rt_engine *e, int32_t stream);
 
 /*
  * One callback for every stream of the batch (analyze.py:234-248 without the shadow
- * filter): `iq` holds n_streams blocks of 2*block_samples interleaved uint8 I,Q bytes,
- * stream s starting at iq + s*stream_stride_bytes.  iq_on_device != 0: `iq` is a device
- * pointer (no copy); otherwise a host pointer (pinned or pageable) that is copied in.
+ * filter): `iq` holds, for every stream, blocks_per_launch consecutive blocks of 2*block_samples
+ * interleaved uint8 I,Q bytes, stream s starting at iq + s*stream_stride_bytes.  iq_on_device != 0:
+ * `iq` is a device pointer (no copy); otherwise a host pointer (pinned or pageable) that is copied in.
  * Blocks until done.  Records come back sorted by (stream, fi, start).
- * On RT_ERR_OVERFLOW *n_out is the number that would have been needed.
+ * On RT_ERR_OVERFLOW *n_out is the number that would have been needed and `out` holds the first
+ * min(max_out, max_records) of them.
  */
 int rt_engine_process(rt_engine *e, const uint8_t *iq, int32_t iq_on_device, size_t stream_stride_bytes,
                       rt_record *out, int32_t max_out, int32_t *n_out);
@@ -131,6 +150,9 @@ int rt_engine_launch(rt_engine *e, const uint8_t *iq, int32_t iq_on_device, size
 /* ... then wait for the OLDEST unfetched launch, copy back and sort its records.  Two launches may be in
  * flight (launch i+1 can be queued before fetch i); a third launch drops the oldest unfetched result. */
 int rt_engine_fetch(rt_engine *e, rt_record *out, int32_t max_out, int32_t *n_out);
+/* Wait for the oldest unfetched launch WITHOUT consuming it: *n_records = the records rt_engine_fetch will return
+ * (callers size their buffer with it). */
+int rt_engine_peek(rt_engine *e, int32_t *n_records);
 
 /*
  * The spectrogram kernels of consecutive launches alternate between two engine-internal streams and the scan kernels (row
@@ -144,7 +166,8 @@ int rt_engine_join(rt_engine *e);
 /* Counters of the last fetched launch: probe hits handed to the extraction kernel, and records emitted. */
 int rt_engine_last_counts(rt_engine *e, int32_t *work_items, int32_t *records);
 
-/* Spectrogram geometry: *T = block_samples / nperseg columns per block. */
+/* Spectrogram geometry: *T = block_samples / nperseg columns per block.  *n_streams counts analyzer units
+ * (streams * blocks_per_launch). */
 int rt_engine_shape(const rt_engine *e, int32_t *n_streams, int32_t *nperseg, int32_t *T);
 
 /*
@@ -164,8 +187,9 @@ int rt_engine_read_row_means(rt_engine *e, int32_t stream, float *out_nperseg);
  */
 int rt_tc256_tables(const double *window, double sample_rate, uint16_t *bmat_out, double *wc_out, double *pscale_out, int32_t *eligible_out);
 
-/* CUDA-event timing of the individual kernels (bench.py roofline). */
-int rt_engine_enable_timing(rt_engine *e, int32_t on);
+/* CUDA-event timing of the individual kernels (bench.py roofline): period = 0 switches it off, k >= 1 brackets the kernels
+ * of every k-th launch (two event records between consecutive spectrogram kernels cost ~5 us of launch gap). */
+int rt_engine_enable_timing(rt_engine *e, int32_t period);
 int rt_engine_get_timing(rt_engine *e, rt_timing *out, int32_t reset);
 
 #ifdef __cplusplus

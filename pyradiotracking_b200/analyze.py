@@ -111,18 +111,45 @@ class Finalized(NamedTuple):
 
 def shadow_mask(ts_us: np.ndarray, dur_us: np.ndarray, max_dbw: np.ndarray) -> np.ndarray:
     """True where a signal is a shadow (analyze.py:283-313): some signal of the same list overlaps
-    it in time (closed intervals, microsecond datetimes) and is strictly louder.  No frequency term."""
+    it in time (closed intervals, microsecond datetimes) and is strictly louder.  No frequency term.
+
+    The reference compares every pair (O(S^2), 18 ms at S = 900).  Signal j overlaps signal i iff it STARTS inside
+    [ts_i, te_i] or its interval CONTAINS ts_i, so the loudest overlapping signal is the maximum of a range-maximum
+    query over the start times (sparse table) and of a stabbing query at ts_i (every interval is a chmax update of a
+    range of start times, written as two power-of-two blocks and pushed down level by level): O(S log S), vectorised."""
     n = len(ts_us)
-    out = np.zeros(n, dtype=bool)
-    if n == 0:
-        return out
-    te = ts_us + dur_us
-    step = max(1, (1 << 22) // n)
-    for i0 in range(0, n, step):
-        sl = slice(i0, min(n, i0 + step))
-        overlap = (ts_us[sl, None] <= te[None, :]) & (te[sl, None] >= ts_us[None, :])
-        out[sl] = (overlap & (max_dbw[None, :] > max_dbw[sl, None])).any(axis=1)
-    return out
+    if n < 2:
+        return np.zeros(n, dtype=bool)
+    ts = np.asarray(ts_us, dtype=np.int64)
+    te = ts + np.asarray(dur_us, dtype=np.int64)
+    mx = np.asarray(max_dbw, dtype=np.float64)
+    U, lo = np.unique(ts, return_inverse=True)            # lo[i]: index of ts[i] among the sorted distinct start times
+    hi = np.searchsorted(U, te, side="right") - 1         # last distinct start time <= te[i] (>= lo[i]: durations are >= 0)
+    m = len(U)
+    K = max(1, int(m).bit_length())
+    st = np.full((K, m), -np.inf)                         # st[k][u] = max over start times u .. u + 2^k - 1
+    np.maximum.at(st[0], lo, mx)
+    for k in range(1, K):
+        h = 1 << (k - 1)
+        st[k] = st[k - 1]
+        st[k, : m - h] = np.maximum(st[k - 1, : m - h], st[k - 1, h:])
+    k = np.frexp((hi - lo + 1).astype(np.float64))[1] - 1     # floor(log2(range length))
+    off = hi - (1 << k) + 1
+    starts_inside = np.maximum(st[k, lo], st[k, off])
+    rt = np.full((K, m), -np.inf)                         # pending chmax updates of the blocks [u, u + 2^k)
+    np.maximum.at(rt, (k, lo), mx)
+    np.maximum.at(rt, (k, off), mx)
+    for kk in range(K - 1, 0, -1):
+        h = 1 << (kk - 1)
+        np.maximum(rt[kk - 1], rt[kk], out=rt[kk - 1])
+        np.maximum(rt[kk - 1, h:], rt[kk, : m - h], out=rt[kk - 1, h:])
+    contains_start = rt[0, lo]
+    return np.maximum(starts_inside, contains_start) > mx
+
+
+# time offset between analyzer units when the shadow filter of a whole batch is evaluated in one pass (2^44 us = 203 days:
+# further apart than any two signals of one callback, so units never overlap)
+_UNIT_GAP_US = 1 << 44
 
 
 class BatchAnalyzer:
@@ -132,16 +159,25 @@ class BatchAnalyzer:
     def __init__(self, devices: Sequence[str], calibration_db: Sequence[float], sample_rate: int, center_freq: int,
                  fft_nperseg: int, fft_window, signal_min_duration_ms: float, signal_max_duration_ms: float,
                  signal_threshold_dbw: float, snr_threshold_db: float, sdr_callback_length: Optional[int] = None,
-                 cuda_device: int = 0, max_records: int = 1 << 16, fft_impl: int = _engine.FFT_AUTO):
+                 cuda_device: int = 0, max_records: int = 0, fft_impl: int = _engine.FFT_AUTO,
+                 scan_schedule: int = _engine.SCAN_AUTO, launch_streams: int = 0, chunk_segs: int = 0,
+                 blocks_per_launch: int = 1):
         self.devices = [str(d) for d in devices]
         self.n_streams = len(self.devices)
         self.calibration_db = [float(c) for c in calibration_db]
         if len(self.calibration_db) != self.n_streams:
             raise ValueError("one calibration value per device")
+        if not isinstance(fft_nperseg, (int, np.integer)) or fft_nperseg < 8 or fft_nperseg > 4096 or fft_nperseg & (fft_nperseg - 1):
+            # scope limit of the CUDA path (scipy takes any length): say so here, not as an EngineError inside the child process
+            raise ValueError(f"fft_nperseg = {fft_nperseg}: the B200 engine supports powers of two in [8, 4096] (see INTEGRATION.md)")
+        if blocks_per_launch < 1:
+            raise ValueError("blocks_per_launch must be >= 1")
         self.sample_rate = sample_rate
         self.center_freq = center_freq
-        self.fft_nperseg = fft_nperseg
+        self.fft_nperseg = int(fft_nperseg)
         self.fft_window = fft_window
+        self.blocks_per_launch = int(blocks_per_launch)
+        self.n_units = self.n_streams * self.blocks_per_launch     # analyzer units per launch (stream-major, block-minor)
         self.block_samples = sample_rate if sdr_callback_length is None else sdr_callback_length   # analyze.py:108-109
         self.signal_min_duration = signal_min_duration_ms / 1000                                    # analyze.py:113
         self.signal_max_duration = signal_max_duration_ms / 1000                                    # analyze.py:114
@@ -152,6 +188,8 @@ class BatchAnalyzer:
         self.cuda_device = cuda_device
         self.max_records = max_records
         self.fft_impl = fft_impl
+        self.scan_schedule, self.launch_streams, self.chunk_segs = scan_schedule, launch_streams, chunk_segs
+        self.timings = {"fetch_wait_s": 0.0, "finalize_s": 0.0, "build_s": 0.0, "collects": 0}   # host-side split of collect()
         self._engine: Optional[_engine.Engine] = None
         self.last_record_count = 0          # candidate records copied back by the last collect()
         self.Signal, self.StateMessage = message_types()
@@ -166,7 +204,9 @@ class BatchAnalyzer:
                 n_streams=self.n_streams, block_samples=self.block_samples, nperseg=self.fft_nperseg, window=self.window,
                 sample_rate=self.sample_rate, signal_threshold=self.signal_threshold, snr_threshold=self.snr_threshold,
                 probe_stride=self.plan.stride, min_cols=self.plan.min_cols, max_cols=self.plan.max_cols,
-                max_records=self.max_records, cuda_device=self.cuda_device, fft_impl=self.fft_impl)
+                max_records=self.max_records, cuda_device=self.cuda_device, fft_impl=self.fft_impl,
+                scan_schedule=self.scan_schedule, launch_streams=self.launch_streams, chunk_segs=self.chunk_segs,
+                blocks_per_launch=self.blocks_per_launch)
         return self._engine
 
     def close(self):
@@ -193,8 +233,8 @@ class BatchAnalyzer:
         ok = ~(duration_s < self.signal_min_duration) & ~(duration_s > self.signal_max_duration)       # :429-433
         r = records[ok]
         start_dt, duration_s = start_dt[ok], duration_s[ok]
-        stream = r["stream"].astype(np.int64)
-        cal = np.asarray(self.calibration_db, dtype=np.float64)[stream]
+        stream = r["stream"].astype(np.int64)                   # analyzer unit = stream * blocks_per_launch + block
+        cal = np.asarray(self.calibration_db, dtype=np.float64)[stream // self.blocks_per_launch]
         mean = r["mean_lin"].astype(np.float64)
         row = r["row_mean"].astype(np.float64)
         with np.errstate(divide="ignore", invalid="ignore"):
@@ -205,35 +245,42 @@ class BatchAnalyzer:
                 max=10 * np.log10(r["max_lin"].astype(np.float64)) - cal, avg=10 * np.log10(mean) - cal,
                 std=r["std_db"].astype(np.float64), noise=10 * np.log10(row), snr=10 * np.log10(mean / row),
                 shadow=np.zeros(len(r), dtype=bool))
-        # shadow filter per stream (signals of one callback share ts_start, so offsets are enough)
-        bounds = np.searchsorted(fin.stream, np.arange(self.n_streams + 1))
-        for s in range(self.n_streams):
-            lo, hi = bounds[s], bounds[s + 1]
-            if hi - lo > 1:
-                fin.shadow[lo:hi] = shadow_mask(fin.ts_off_us[lo:hi], fin.dur_us[lo:hi], fin.max[lo:hi])
+        # shadow filter per analyzer unit (signals of one callback share ts_start, so offsets are enough): one pass over the
+        # whole batch, the units shifted so far apart in time that they cannot overlap
+        if len(r) > 1:
+            fin.shadow[:] = shadow_mask(fin.ts_off_us + fin.stream * _UNIT_GAP_US, fin.dur_us, fin.max)
         return fin
 
+    def unit_ts(self, ts_start: Sequence[datetime.datetime]) -> List[datetime.datetime]:
+        """ts_start of every analyzer unit: block b of a launch starts b callback lengths after the stream's first block
+        (the reference advances `_ts` by `timedelta(seconds=len(buffer) / sample_rate)` per callback, analyze.py:205,221)."""
+        if self.blocks_per_launch == 1:
+            return list(ts_start)
+        dt = datetime.timedelta(seconds=self.block_samples / self.sample_rate)
+        return [t + b * dt for t in ts_start for b in range(self.blocks_per_launch)]
+
     def build_signals(self, fin: "Finalized", ts_start: Sequence[datetime.datetime], keep: Optional[np.ndarray] = None):
-        """Signal objects per stream, in the reference's emission order (bin, then time), for the rows of
-        `fin` selected by `keep` (default: all)."""
-        out = [[] for _ in range(self.n_streams)]
-        Signal, devices = self.Signal, self.devices
+        """Signal objects per analyzer unit, in the reference's emission order (bin, then time), for the rows of
+        `fin` selected by `keep` (default: all).  `ts_start`: one per stream (the first block of the launch)."""
+        out = [[] for _ in range(self.n_units)]
+        Signal, devices, bpl = self.Signal, self.devices, self.blocks_per_launch
+        uts = self.unit_ts(ts_start)
         idx = np.arange(len(fin.stream)) if keep is None else np.nonzero(keep)[0]
         td = datetime.timedelta
-        for i, s, off, dur, f, mx, av, sd, no, sn in zip(
-                idx.tolist(), fin.stream[idx].tolist(), fin.ts_off_us[idx].tolist(), fin.dur_us[idx].tolist(),
+        for u, off, dur, f, mx, av, sd, no, sn in zip(
+                fin.stream[idx].tolist(), fin.ts_off_us[idx].tolist(), fin.dur_us[idx].tolist(),
                 fin.frequency[idx].tolist(), fin.max[idx].tolist(), fin.avg[idx].tolist(), fin.std[idx].tolist(),
                 fin.noise[idx].tolist(), fin.snr[idx].tolist()):
-            ts = (ts_start[s] + td(microseconds=off)).astimezone(UTC)
-            out[s].append(Signal(devices[s], ts, f, td(microseconds=dur), mx, av, sd, no, sn))
+            ts = (uts[u] + td(microseconds=off)).astimezone(UTC)
+            out[u].append(Signal(devices[u // bpl], ts, f, td(microseconds=dur), mx, av, sd, no, sn))
         return out
 
     def finalize(self, records: np.ndarray, ts_start: Sequence[datetime.datetime]):
-        """-> per stream `(signals, keys)`: the reference's `extract_signals` output (analyze.py:419-450)
+        """-> per analyzer unit `(signals, keys)`: the reference's `extract_signals` output (analyze.py:419-450)
         in its order (bin, then time) and the integer `(fi, start, end)` of each."""
         fin = self.finalize_arrays(records)
         sigs = self.build_signals(fin, ts_start)
-        keys = [[] for _ in range(self.n_streams)]
+        keys = [[] for _ in range(self.n_units)]
         for s, k in zip(fin.stream.tolist(), zip(fin.fi.tolist(), fin.start.tolist(), fin.end.tolist())):
             keys[s].append(k)
         return list(zip(sigs, keys))
@@ -257,29 +304,40 @@ class BatchAnalyzer:
         self.engine.launch(iq)
 
     def collect(self, ts_start: Sequence[datetime.datetime], with_all: bool = False):
-        """Wait for the oldest submission.  -> per stream `(filtered_signals, n_before_filter)`, or with
-        `with_all` `(filtered_signals, all_signals, keys)` like `process_blocks`."""
+        """Wait for the oldest submission.  -> per analyzer unit (= per stream when `blocks_per_launch` is 1; otherwise stream-major,
+        block-minor) `(filtered_signals, n_before_filter)`, or with `with_all` `(filtered_signals, all_signals, keys)` like
+        `process_blocks`.  `ts_start`: one per stream, the start of the first block of the launch."""
+        t0 = time.perf_counter()
         records = self.engine.fetch()
+        t1 = time.perf_counter()
         self.last_record_count = len(records)
         fin = self.finalize_arrays(records)
+        t2 = time.perf_counter()
         if not with_all:
             kept = self.build_signals(fin, ts_start, ~fin.shadow)
-            counts = np.bincount(fin.stream, minlength=self.n_streams)
-            return [(kept[s], int(counts[s])) for s in range(self.n_streams)]
-        sigs = self.build_signals(fin, ts_start)
-        keys = [[] for _ in range(self.n_streams)]
-        kept = [[] for _ in range(self.n_streams)]
-        pos = [0] * self.n_streams
-        for s, sh, k in zip(fin.stream.tolist(), fin.shadow.tolist(), zip(fin.fi.tolist(), fin.start.tolist(), fin.end.tolist())):
-            keys[s].append(k)
-            if not sh:
-                kept[s].append(sigs[s][pos[s]])      # the very objects of `sigs`, in order
-            pos[s] += 1
-        return [(kept[s], sigs[s], keys[s]) for s in range(self.n_streams)]
+            counts = np.bincount(fin.stream, minlength=self.n_units)
+            out = [(kept[u], int(counts[u])) for u in range(self.n_units)]
+        else:
+            sigs = self.build_signals(fin, ts_start)
+            keys = [[] for _ in range(self.n_units)]
+            kept = [[] for _ in range(self.n_units)]
+            pos = [0] * self.n_units
+            for s, sh, k in zip(fin.stream.tolist(), fin.shadow.tolist(), zip(fin.fi.tolist(), fin.start.tolist(), fin.end.tolist())):
+                keys[s].append(k)
+                if not sh:
+                    kept[s].append(sigs[s][pos[s]])      # the very objects of `sigs`, in order
+                pos[s] += 1
+            out = [(kept[u], sigs[u], keys[u]) for u in range(self.n_units)]
+        tm = self.timings
+        tm["fetch_wait_s"] += t1 - t0
+        tm["finalize_s"] += t2 - t1
+        tm["build_s"] += time.perf_counter() - t2
+        tm["collects"] += 1
+        return out
 
     def process_blocks(self, iq, ts_start: Sequence[datetime.datetime]):
-        """`iq`: uint8 `[n_streams, 2*block_samples]` on the host, or a CUDA tensor of that shape.
-        -> per stream `(filtered_signals, all_signals, keys)`."""
+        """`iq`: uint8 `[n_streams, 2*block_samples]` (`[n_streams, blocks_per_launch, 2*block_samples]`) on the host, or a
+        CUDA tensor of that shape.  -> per analyzer unit `(filtered_signals, all_signals, keys)`."""
         self.submit(iq)
         return self.collect(ts_start, with_all=True)
 
@@ -353,7 +411,7 @@ class SignalAnalyzer(multiprocessing.Process):
             fft_impl=kwargs.get("fft_impl", _engine.FFT_AUTO))
         self._batch: Optional[BatchAnalyzer] = None
         self._ts = None
-        self._have_last = False         # stands in for `_spectrogram_last is not None` (the carry lives on the device)
+        self._have_last = False         # `_spectrogram_last is not None` (the carry itself lives on the device)
         self._alarm_armed = False
         self.last_state = None
         self.sdr = None
@@ -365,6 +423,15 @@ class SignalAnalyzer(multiprocessing.Process):
         if self._batch is None:
             self._batch = BatchAnalyzer(**self._batch_args)
         return self._batch
+
+    @property
+    def _spectrogram_last(self) -> Optional[np.ndarray]:
+        """The reference's side state (analyze.py:128,268): the previous block's spectrogram as scipy returns it, float64
+        `(fft_nperseg, T)`, or None before the first callback.  The carry the engine uses stays on the device (fp32); this
+        copies it back on demand, for callers that inspect it."""
+        if not self._have_last:
+            return None
+        return self.batch.engine.read_spectrogram(0).T.astype(np.float64)
 
     # -- process entry (analyze.py:131-157) ------------------------------------------------------
     def run(self):
@@ -446,18 +513,34 @@ class SignalAnalyzer(multiprocessing.Process):
             # a changing block length is undefined there, and the engine is sized for one length
             raise ValueError(f"callback delivered {n_samples} samples, analyzer is configured for {self.sdr_callback_length}")
 
+        batch = self.batch
+        tm0 = dict(batch.timings)
         bench_start = time.time()
-        filtered, signals, _ = self.batch.process_blocks(raw.reshape(1, -1), [ts_start])[0]
-        bench_extract = time.time()
+        filtered, signals, _ = batch.process_blocks(raw.reshape(1, -1), [ts_start])[0]
+        bench_filter = time.time()
         [self.consume_signal(s) for s in filtered]
         bench_consume = time.time()
         self._have_last = True
+        tm = batch.timings
+        t_device = tm["fetch_wait_s"] - tm0["fetch_wait_s"]             # H2D copy + kernels + D2H of the records
+        t_final = (tm["finalize_s"] - tm0["finalize_s"]) + (tm["build_s"] - tm0["build_s"])
+        # Same line and fields as analyze.py:254-260 -- including its unit quirk (seconds x 100 printed as "ms") so that anything
+        # parsing the reference's log keeps working -- followed by the CUDA path's own split in real milliseconds.
         logger.info(
-            f"SDR {self.device} recv {n_samples}, clock drift: {clock_drift:.2f} s, "
-            f"filtered {len(filtered)} / {len(signals)} signals, block len: {buffer_len_dt.total_seconds() * 1000:.1f} ms, "
-            f"compute: {(bench_consume - bench_start) * 1000:.1f} ms")
-        logger.debug(f"timings - device+finalise: {(bench_extract - bench_start) * 1000:.1f} ms, "
-                     f"consume: {(bench_consume - bench_extract) * 1000:.1f} ms")
+            f"SDR {self.device} recv {n_samples}, "
+            + f"clock drift: {clock_drift:.2f} s, "
+            + f"filtered {len(filtered)} / {len(signals)} signals, "
+            + f"block len: {(buffer_len_dt.total_seconds())*100:.1f} ms, "
+            + f"compute: {(bench_consume-bench_start)*100:.1f} ms, "
+            + f"cuda: device {t_device * 1e3:.2f} ms, finalise {t_final * 1e3:.2f} ms"
+        )
+        # analyze.py:262-267: the spectrogram and the scans are one device step here; "filter" is part of the finaliser
+        logger.debug(
+            f"timings - spectogram: {t_device*100:.1f} ms, "
+            + f"extract: {t_final*100:.1f} ms, "
+            + f"filter: {max(0.0, bench_filter - bench_start - t_device - t_final)*100:.1f} ms, "
+            + f"consume: {(bench_consume-bench_filter)*100:.1f} ms"
+        )
 
     def consume_signal(self, signal):
         """analyze.py:270-280."""

@@ -64,10 +64,9 @@ __device__ __forceinline__ bool above(float p, float thr, float avg, float snr) 
 //                                  half-warp stores its bins as four float4, each store instruction 256 contiguous bytes
 //   TILE   (tensor-core kernel)    S[stream][t / 32][quad][t % 32][4], quad = 4 k1 + (k2 >> 2) (rt::tile_cell_off): a thread owns a
 //                                  segment, a warp stores 512 contiguous bytes, 32 time steps of a bin lie within 512 bytes
-//   PERM64 (register kernel, default) S[stream][t / 64][pos / 8][t % 64][pos % 8]: PERM positions, time-blocked -- a walk along time reads
-//                                  consecutive 32-byte sectors (2 KB per 64 steps) instead of one sector per 1 KB row
-enum { LAYOUT_LINEAR = 0, LAYOUT_PERM = 1, LAYOUT_TILE = 2, LAYOUT_PERM64 = 3, LAYOUT_PERM64W = 4 };   // PERM64W: blocks of 32 positions
-__host__ __device__ constexpr bool layout_is_perm(int L) { return L == LAYOUT_PERM || L == LAYOUT_PERM64 || L == LAYOUT_PERM64W; }
+// (time-blocked variants of PERM were measured and rejected: DESIGN.md 5.7)
+enum { LAYOUT_LINEAR = 0, LAYOUT_PERM = 1, LAYOUT_TILE = 2 };
+__host__ __device__ constexpr bool layout_is_perm(int L) { return L == LAYOUT_PERM; }
 
 struct CellRef {
     const float* base;     // stream base + the bin's constant part
@@ -77,22 +76,12 @@ struct CellRef {
         CellRef c;
         if (L == LAYOUT_TILE) { c.base = S + (size_t)s * stream_stride + (size_t)((fi & 15) * 4 + (fi >> 6)) * 128 + ((fi >> 4) & 3); c.step = 0; }
         else if (L == LAYOUT_PERM) { c.base = S + (size_t)s * stream_stride + (((fi >> 6) << 6) | ((fi & 15) << 2) | ((fi >> 4) & 3)); c.step = 256; }
-        else if (L == LAYOUT_PERM64) {
-            const int pos = ((fi >> 6) << 6) | ((fi & 15) << 2) | ((fi >> 4) & 3);
-            c.base = S + (size_t)s * stream_stride + (pos >> 3) * 512 + (pos & 7); c.step = 0;
-        }
-        else if (L == LAYOUT_PERM64W) {
-            const int pos = ((fi >> 6) << 6) | ((fi & 15) << 2) | ((fi >> 4) & 3);
-            c.base = S + (size_t)s * stream_stride + (pos >> 5) * 2048 + (pos & 31); c.step = 0;
-        }
         else { c.base = S + (size_t)s * stream_stride + fi; c.step = n; }
         return c;
     }
     template <int L>
     __device__ __forceinline__ float at(int t) const {
-        return L == LAYOUT_TILE ? base[(size_t)(t >> 5) * 8192 + (size_t)(t & 31) * 4]
-             : L == LAYOUT_PERM64 ? base[((size_t)(t >> 6) << 14) + ((t & 63) << 3)]
-             : L == LAYOUT_PERM64W ? base[((size_t)(t >> 6) << 14) + ((t & 63) << 5)] : base[(size_t)t * step];
+        return L == LAYOUT_TILE ? base[(size_t)(t >> 5) * 8192 + (size_t)(t & 31) * 4] : base[(size_t)t * step];
     }
 };
 
@@ -117,7 +106,7 @@ __global__ void __launch_bounds__(NT) spectro_generic(SpectroArgs a) {
     for (int i = tid; i < n; i += NT) rowacc[i] = 0.f;
 
     for (int seg = seg0; seg < seg1; ++seg) {
-        const uchar2* src = reinterpret_cast<const uchar2*>(a.iq + (size_t)s * a.stream_stride + (size_t)seg * 2 * n);
+        const uchar2* src = reinterpret_cast<const uchar2*>(a.unit_base(s) + (size_t)seg * 2 * n);
         if (tid == 0) sums[0] = sums[1] = 0;
         __syncthreads();
         // scipy detrend='constant': the segment's complex mean; byte sums are exact integers
@@ -254,7 +243,6 @@ __global__ void __launch_bounds__(128, 16) row_mean_kernel(const float* part, fl
 struct ScanArgs {
     const float* S;        // current block (LINEAR or TILE layout)
     const float* Sprev;    // previous block
-    const float* P;        // probe plane [stream][n_probes][256] in PERM order (register kernel), or nullptr: probe S itself
     size_t stream_stride;  // floats per stream
     float* avg;            // [stream][n] row means: written by the probe kernel (from `part`) or by the tensor-core kernel
     const float* part;     // [stream][n_chunks][n] chunk row sums (nullptr: avg is already there)
@@ -262,6 +250,7 @@ struct ScanArgs {
     int n_chunks;
     const float* thr;      // [stream]
     const int* has_prev;   // [stream]
+    int bpl;               // blocks per launch: the carry of unit s is unit s - 1 of the same buffer unless s % bpl == 0
     float snr;
     int n, T, stride, n_probes, min_cols, max_cols;
     int n_streams_scan;    // streams of the batch (lean probe kernel: tiles are walked with a grid stride)
@@ -312,12 +301,7 @@ __global__ void probe_kernel(ScanArgs a) {
     if (active) {
         // ~96 % of the probe cells fail the predicate: only a hit pays for its neighbours
         float c0[PPT];
-        if (layout_is_perm(TILE) && a.P != nullptr) {
-            // the register kernel left a dense copy of the probe columns: a warp reads 128 contiguous bytes per load
-            const float* prow = a.P + ((size_t)s * a.n_probes + (size_t)g * PPT) * 256 + idx;
-#pragma unroll
-            for (int i = 0; i < PPT; ++i) c0[i] = (g * PPT + i < a.n_probes) ? prow[(size_t)i * 256] : -1.f;
-        } else {
+        {
             const CellRef col = CellRef::make<TILE>(a.S, a.stream_stride, s, fi, a.n);
 #pragma unroll
             for (int i = 0; i < PPT; ++i) {
@@ -414,16 +398,10 @@ __global__ void __launch_bounds__(128, 16) probe_lean_kernel(ScanArgs a) {
         const int fi = layout_is_perm(TILE) ? ((idx >> 2) & 15) + 16 * (4 * (idx >> 6) + (idx & 3)) : idx;
         const CellRef col = CellRef::make<TILE>(a.S, a.stream_stride, s, fi, a.n);
         float c0[LEAN_PPT];
-        if (layout_is_perm(TILE) && a.P != nullptr) {
-            const float* prow = a.P + ((size_t)s * a.n_probes + (size_t)g * LEAN_PPT) * 256 + idx;
 #pragma unroll
-            for (int i = 0; i < LEAN_PPT; ++i) c0[i] = (g * LEAN_PPT + i < a.n_probes) ? prow[(size_t)i * 256] : -1.f;
-        } else {
-#pragma unroll
-            for (int i = 0; i < LEAN_PPT; ++i) {
-                const int k = g * LEAN_PPT + i;
-                c0[i] = (k < a.n_probes) ? col.at<TILE>(k * a.stride) : -1.f;
-            }
+        for (int i = 0; i < LEAN_PPT; ++i) {
+            const int k = g * LEAN_PPT + i;
+            c0[i] = (k < a.n_probes) ? col.at<TILE>(k * a.stride) : -1.f;
         }
         const float thr = a.thr[s], avg = a.avg[s * a.n + fi];
         const Pred pred(thr, avg, snr);
@@ -492,7 +470,11 @@ __global__ void __launch_bounds__(MINB > 0 ? 128 : 1024, MINB > 0 ? MINB : 1) ex
         const uint2 wk = a.work[item];
         const int s = wk.x >> 16, fi = wk.x & 0xffff, ti0 = (int)(wk.y & 0xffffffu), members = (int)(wk.y >> 24) + 1;
         const CellRef col = CellRef::make<TILE>(a.S, a.stream_stride, s, fi, n);
-        const CellRef pcol = CellRef::make<TILE>(a.Sprev, a.stream_stride, s, fi, n);
+        // carry (analyze.py:383-398): the previous block of this stream is the previous unit of the same launch, or -- for
+        // the first block of a launch -- the last unit of the stream in the previous launch's buffer
+        const bool first_blk = a.bpl == 1 || (s % a.bpl) == 0;
+        const CellRef pcol = first_blk ? CellRef::make<TILE>(a.Sprev, a.stream_stride, s + a.bpl - 1, fi, n)
+                                       : CellRef::make<TILE>(a.S, a.stream_stride, s - 1, fi, n);
         const float thr = a.thr[s], avg = a.avg[s * n + fi], snr = a.snr;
         const Pred pred(thr, avg, snr);
         int skip_to = 0;                                 // every cell in [previous member's probe, skip_to) is known to be above
@@ -673,44 +655,41 @@ struct rt_engine {
     int dev = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    int n = 0, T = 0, n_streams = 0, n_chunks = 0, chunk_segs = 0, n_probes = 0;
-    bool reg256 = false;                     // nperseg 256: register kernel (v7) or tensor-core kernel; TILE layout
-    bool tc256 = false;                      // tensor-core stage 1 (spectro_tc256.cuh)
-    int t64 = 0;                             // register kernel writes a time-blocked layout: positions per block (0 = row-major, 8, 32)
+    int n = 0, T = 0, n_streams = 0, bpl = 1, n_units = 0, n_chunks = 0, chunk_segs = 0, n_probes = 0;
+    size_t block_bytes = 0;
+    int max_records = 0;                     // effective capacity of one launch's record list
+    bool reg256 = false;                     // nperseg 256: register kernel (v7n) or tensor-core kernel
+    bool tc256 = false;                      // tensor-core stage 1 (spectro_tc256.cuh), TILE layout
     bool r16 = false;                        // nperseg 1024 / 4096: radix-16 Stockham kernel (spectro_r16.cuh), LINEAR layout
-    size_t s_stride = 0;                     // floats per stream in a spectrogram buffer
+    size_t s_stride = 0;                     // floats per unit in a spectrogram buffer
     float pscale = 1.f;                      // power factor carried by S / row means / thresholds (tensor-core path), a power of two
     uint4* d_bmat = nullptr;                 // tensor-core operand image
     rt::TcTables tc_tab;
     int tc_grid = 0, tc_slots = 1, tc_bps = 0;
-    int extract_minb = 0;                    // RT_EXTRACT_MINB: 0 (no register cap), 12 or 16 resident 128-thread CTAs per SM
-    int probe_ppt = PROBE_PPT;               // probe columns per thread: 8, 16 or 32 (RT_PROBE_PPT)
-    int probe_threads = 256, extract_threads = 128, extract_ctas = 148 * 24;   // scan launch shapes (RT_SCAN_SHAPE=probe,extract,ctas)
-    int v7_maxr = -1;                        // RT_V7_MAXR: -1 = launch bounds + pinned addresses (default), 0 = launch bounds, 112 / 104 / 96 = register cap
-    bool scan_lean = false;                  // two-stream schedule: 32-register scan CTAs that fit beside the resident spectrogram CTAs
+    int probe_ppt = PROBE_PPT;               // probe columns per thread: 8, 16 or 32 (chosen by launch size)
+    bool scan_lean = false;                  // RT_SCAN_LEAN: 32-register scan CTAs that fit beside the resident spectrogram CTAs
     int lean_ctas = 148;
-    int lean_ex = 10;                        // lean extraction windows: 10 = <1, 0> (default: fewest sectors), 20 = <2, 0>, 22 = <2, 2> (RT_LEAN_EX)
     float* d_win = nullptr;
     float2* d_tw = nullptr;
     // three spectrogram buffers: launch i writes S[i % 3] while the scan of launch i-1 still reads
     // S[(i-1) % 3] (its block) and S[(i-2) % 3] (its carry) on the scan stream
     float* d_S[RT_SBUFS] = {nullptr, nullptr, nullptr};
     int cur = 0;
-    float* d_part[2] = {nullptr, nullptr};   // chunk row sums, by launch parity
-    float* d_probe[2] = {nullptr, nullptr};  // probe plane (register kernel), by launch parity
+    float* d_part[RT_SLOTS] = {nullptr, nullptr};   // chunk row sums, by launch parity
+    float* d_avg[RT_SLOTS] = {nullptr, nullptr};    // row means, by launch parity
+    unsigned* d_ctr[RT_SLOTS] = {nullptr, nullptr}; // tensor-core kernel: finished-run tickets per unit, by launch parity (two launches
+                                                    // may overlap on the two launch streams: they must not share tickets)
     cudaStream_t scan_stream = nullptr;      // row mean / probe / extract: overlaps the next launch's spectrogram
     // Consecutive spectrogram kernels alternate between two internal streams (forked from the launch stream by an event), so
     // that launch i+1 fills the SMs while the last CTAs of launch i drain: step 227.7 -> 213.9 us at config 2
-    // (RT_LAUNCH_STREAMS=1: spectrogram kernels on the launch stream itself)
     cudaStream_t lstream[2] = {nullptr, nullptr};
     cudaEvent_t fork_ev = nullptr;
     int n_lstreams = 1;
-    cudaEvent_t spec_done[2] = {nullptr, nullptr};
-    float* d_avg[2] = {nullptr, nullptr};    // row means, by launch parity (written by the spectrogram kernel)
-    unsigned* d_ctr = nullptr;               // [n_streams] finished-CTA tickets of the spectrogram kernel
-    float* d_thr = nullptr;
-    int* d_hasprev = nullptr;
-    std::vector<int> h_hasprev;
+    cudaEvent_t spec_done[RT_SLOTS] = {nullptr, nullptr};
+    float* d_thr = nullptr;                  // [unit]
+    int* d_hasprev = nullptr;                // [unit]
+    std::vector<int> h_hasprev;              // [stream]: a previous launch exists (the carry of the first block of a launch)
+    std::vector<int> h_hasprev_units;
     bool hasprev_dirty = true;
     // host input: two staging buffers filled on an upload stream, so the copy of launch i+1 overlaps the kernels of launch i
     uint8_t* d_stage[2] = {nullptr, nullptr};
@@ -721,17 +700,18 @@ struct rt_engine {
     uint2* d_work = nullptr;
     // results ring: up to RT_SLOTS launches may be in flight before their records are fetched
     int* d_counters = nullptr;              // [slot][2]
-    rt_record* d_rec[2] = {nullptr, nullptr};
-    cudaEvent_t done[2] = {nullptr, nullptr};
+    rt_record* d_rec[RT_SLOTS] = {nullptr, nullptr};
+    cudaEvent_t done[RT_SLOTS] = {nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;
     unsigned long long launch_seq = 0, fetch_seq = 0;
-    rt_record* h_rec = nullptr;     // pinned
+    rt_record* h_rec = nullptr;     // pinned, grown on demand
+    size_t h_rec_cap = 0;
     int* h_counters = nullptr;      // pinned
+    bool peeked = false;            // h_counters holds the counters of the oldest unfetched launch
     float* d_tmp = nullptr;         // parity hook scratch
     bool launched = false;
     int last_work_items = 0, last_records = 0;   // counters of the last fetched launch
     // timing
-    bool timing = false;
     struct EvSet { cudaEvent_t ev[6]; };   // launch stream: before / after spectrogram; scan stream: start, row mean, probe, extract
     std::vector<EvSet> ev_pool;
     size_t ev_used = 0;
@@ -739,7 +719,7 @@ struct rt_engine {
     // Per-kernel events are recorded on every timing_period-th launch only: two event records between consecutive spectrogram
     // kernels cost ~5 us of launch gap per step (232 -> 227 us at config 2).  The per-kernel sums reported by
     // rt_engine_get_timing are scaled to all launches (sum over the timed ones x launches / timed launches).
-    int timing_period = 4;
+    int timing_period = 0;                 // 0: off
     int64_t timed_launches = 0, timing_launches = 0;      // launches with events / launches while timing was on
 };
 
@@ -748,6 +728,7 @@ namespace {
 int harvest_timing(rt_engine* e) {
     if (e->ev_used == 0) return RT_OK;
     CU(cudaStreamSynchronize(e->stream));
+    for (auto& ls : e->lstream) if (ls) CU(cudaStreamSynchronize(ls));
     if (e->scan_stream) CU(cudaStreamSynchronize(e->scan_stream));
     for (size_t i = 0; i < e->ev_used; ++i) {
         float ms[4];
@@ -766,15 +747,19 @@ void free_engine(rt_engine* e) {
     if (!e) return;
     cudaSetDevice(e->dev);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    for (auto& ls : e->lstream) if (ls) cudaStreamSynchronize(ls);
     if (e->scan_stream) cudaStreamSynchronize(e->scan_stream);
+    if (e->h2d_stream) cudaStreamSynchronize(e->h2d_stream);
+    if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     for (auto& s : e->ev_pool)
         for (auto& ev : s.ev) cudaEventDestroy(ev);
     cudaFree(e->d_win); cudaFree(e->d_tw);
     for (auto& p : e->d_S) cudaFree(p);
-    cudaFree(e->d_part[0]); cudaFree(e->d_part[1]); cudaFree(e->d_probe[0]); cudaFree(e->d_probe[1]); cudaFree(e->d_avg[0]); cudaFree(e->d_avg[1]); cudaFree(e->d_ctr); cudaFree(e->d_bmat); cudaFree(e->d_thr); cudaFree(e->d_hasprev);
-    cudaFree(e->d_stage[0]); cudaFree(e->d_stage[1]); cudaFree(e->d_work);
+    for (int k = 0; k < RT_SLOTS; ++k) { cudaFree(e->d_part[k]); cudaFree(e->d_avg[k]); cudaFree(e->d_ctr[k]); cudaFree(e->d_rec[k]); }
+    cudaFree(e->d_bmat); cudaFree(e->d_thr); cudaFree(e->d_hasprev);
+    cudaFree(e->d_stage[0]); cudaFree(e->d_stage[1]); cudaFree(e->d_work); cudaFree(e->d_counters); cudaFree(e->d_tmp);
     for (int k = 0; k < 2; ++k) { if (e->h2d_done[k]) cudaEventDestroy(e->h2d_done[k]); if (e->stage_free[k]) cudaEventDestroy(e->stage_free[k]); }
-    if (e->h2d_stream) cudaStreamDestroy(e->h2d_stream); cudaFree(e->d_counters); cudaFree(e->d_rec[0]); cudaFree(e->d_rec[1]); cudaFree(e->d_tmp);
+    if (e->h2d_stream) cudaStreamDestroy(e->h2d_stream);
     for (auto& ev : e->done) if (ev) cudaEventDestroy(ev);
     for (auto& ev : e->spec_done) if (ev) cudaEventDestroy(ev);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -785,6 +770,18 @@ void free_engine(rt_engine* e) {
     if (e->h_counters) cudaFreeHost(e->h_counters);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
+}
+
+// wait for the oldest unfetched launch and read its two counters (work items, records)
+int peek_oldest(rt_engine* e) {
+    if (e->peeked) return RT_OK;
+    const int slot = (int)(e->fetch_seq % RT_SLOTS);
+    // copy on a side stream that only waits for THIS launch, so a later launch already queued does not delay it
+    CU(cudaStreamWaitEvent(e->copy_stream, e->done[slot], 0));
+    CU(cudaMemcpyAsync(e->h_counters, e->d_counters + 2 * slot, 2 * sizeof(int), cudaMemcpyDeviceToHost, e->copy_stream));
+    CU(cudaStreamSynchronize(e->copy_stream));
+    e->peeked = true;
+    return RT_OK;
 }
 
 }  // namespace
@@ -808,12 +805,22 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     const int n = cfg->nperseg;
     if (n < 8 || n > 4096 || (n & (n - 1))) return fail(RT_ERR_INVALID, "nperseg must be a power of two in [8, 4096]");
     if (cfg->n_streams < 1 || cfg->n_streams > 65535) return fail(RT_ERR_INVALID, "n_streams must be in [1, 65535]");
+    const int bpl = cfg->blocks_per_launch == 0 ? 1 : cfg->blocks_per_launch;
+    if (bpl < 1 || (long long)cfg->n_streams * bpl > 65535) return fail(RT_ERR_INVALID, "blocks_per_launch must be >= 1 and n_streams * blocks_per_launch <= 65535");
     if (!cfg->window || !cfg->signal_threshold) return fail(RT_ERR_INVALID, "window / signal_threshold missing");
     if (cfg->block_samples / n < 2) return fail(RT_ERR_INVALID, "block_samples must hold at least two segments (analyze.py:354 indexes times[1])");
     if (cfg->block_samples / n > (1 << 24)) return fail(RT_ERR_INVALID, "block too long");
-    if (cfg->probe_stride < 1 || cfg->min_cols < 0 || cfg->max_cols < cfg->min_cols || cfg->max_records < 1)
+    if (cfg->probe_stride < 1 || cfg->min_cols < 0 || cfg->max_cols < cfg->min_cols || cfg->max_records < 0)
         return fail(RT_ERR_INVALID, "probe_stride / min_cols / max_cols / max_records out of range");
     if (!(cfg->sample_rate > 0) || !(cfg->snr_threshold >= 0)) return fail(RT_ERR_INVALID, "sample_rate / snr_threshold out of range");
+    if (cfg->fft_impl < RT_FFT_AUTO || cfg->fft_impl > RT_FFT_TC256) return fail(RT_ERR_INVALID, "unknown fft_impl");
+    if ((cfg->fft_impl == RT_FFT_REG256 || cfg->fft_impl == RT_FFT_TC256) && n != 256) return fail(RT_ERR_INVALID, "RT_FFT_REG256 / RT_FFT_TC256 need nperseg == 256");
+    if (cfg->scan_schedule < RT_SCAN_AUTO || cfg->scan_schedule > RT_SCAN_LEAN) return fail(RT_ERR_INVALID, "unknown scan_schedule");
+    if (cfg->launch_streams < 0 || cfg->launch_streams > 2) return fail(RT_ERR_INVALID, "launch_streams must be 0 (auto), 1 or 2");
+    if (cfg->launch_streams == 2 && cfg->scan_schedule == RT_SCAN_SERIAL) return fail(RT_ERR_INVALID, "two launch streams need an overlapped scan schedule");
+    if (cfg->chunk_segs < 0 || cfg->chunk_segs % 8 != 0) return fail(RT_ERR_INVALID, "chunk_segs must be 0 (auto) or a multiple of 8");
+    if (cfg->fft_impl == RT_FFT_TC256 && bpl != 1) return fail(RT_ERR_INVALID, "RT_FFT_TC256 does not take blocks_per_launch > 1");
+    for (int r : cfg->reserved) if (r != 0) return fail(RT_ERR_INVALID, "rt_config.reserved must be zero");
 
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
@@ -830,49 +837,41 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     e->n = n;
     e->T = (int)(cfg->block_samples / n);
     e->n_streams = cfg->n_streams;
+    e->bpl = bpl;
+    e->n_units = cfg->n_streams * bpl;
+    e->block_bytes = 2 * (size_t)cfg->block_samples;
     e->n_probes = (e->T + cfg->probe_stride - 1) / cfg->probe_stride;
-    if ((cfg->fft_impl == RT_FFT_REG256 || cfg->fft_impl == RT_FFT_TC256) && n != 256) { delete e; return fail(RT_ERR_INVALID, "RT_FFT_REG256 / RT_FFT_TC256 need nperseg == 256"); }
-    if (cfg->fft_impl < RT_FFT_AUTO || cfg->fft_impl > RT_FFT_TC256) { delete e; return fail(RT_ERR_INVALID, "unknown fft_impl"); }
     e->reg256 = (n == 256) && (cfg->fft_impl != RT_FFT_GENERIC);
     e->tc256 = cfg->fft_impl == RT_FFT_TC256;
     e->r16 = (n == 1024 || n == 4096) && cfg->fft_impl == RT_FFT_AUTO;
-    e->chunk_segs = e->reg256 ? 256 : 32;
+    e->chunk_segs = 32;
     if (e->reg256) {
-        // short blocks (300 kS/s SDRs, replay): shorter chunks = more CTAs per stream.  The choice depends on T only, so a
+        // short blocks (300 kS/s SDRs, replay): shorter chunks = more CTAs per unit.  The choice depends on T only, so a
         // stream gives bit-identical row means whether it runs alone or inside a batch.
         e->chunk_segs = e->T >= 8192 ? 192 : (e->T >= 2048 ? 128 : 64);   // 192 at T = 9375 (49 chunks per stream): step 205.0 -> 202.8 us vs 128, 209.8 at 256
+        if (cfg->chunk_segs > 0) e->chunk_segs = cfg->chunk_segs;
     }
-    if (const char* cs = std::getenv("RT_CHUNK_SEGS")) { const int v = std::atoi(cs); if (e->reg256 && v >= 8 && v % 8 == 0) e->chunk_segs = v; }
-    if (const char* mb = std::getenv("RT_EXTRACT_MINB")) { const int v = std::atoi(mb); if (v == 0 || v == 12 || v == 16) e->extract_minb = v; }
     {
         // small launches (a single wideband stream): fewer probe columns per thread = more CTAs; 32 columns per thread would
         // leave a 20 MS/s nperseg-1024 block with 16 probe CTAs, each a long chain of dependent round trips
         const long long bin_blocks = (n + 255) / 256;
         for (int ppt = 32; ppt >= 8; ppt >>= 1) {
             e->probe_ppt = ppt;
-            if (bin_blocks * ((e->n_probes + ppt - 1) / ppt) * e->n_streams >= 2 * 148) break;
+            if (bin_blocks * ((e->n_probes + ppt - 1) / ppt) * e->n_units >= 2 * 148) break;
         }
-    }
-    if (const char* pp = std::getenv("RT_PROBE_PPT")) { const int v = std::atoi(pp); if (v == 8 || v == 16 || v == 32) e->probe_ppt = v; }
-    if (const char* sh = std::getenv("RT_SCAN_SHAPE")) {
-        int a = 0, b = 0, c = 0;
-        if (std::sscanf(sh, "%d,%d,%d", &a, &b, &c) == 3 && a >= 32 && a <= 1024 && a % 32 == 0 && b >= 32 && b <= 1024 && b % 32 == 0 && c >= 1) { e->probe_threads = a; e->extract_threads = b; e->extract_ctas = c; }
     }
     e->n_chunks = (e->T + e->chunk_segs - 1) / e->chunk_segs;
     if (e->r16) {
-        // segments are dealt round-robin over n_chunks CTAs (x teams) per stream; 296 = 148 SMs x 2 resident CTAs
+        // segments are dealt round-robin over n_chunks CTAs (x teams) per unit; 296 = 148 SMs x 2 resident CTAs
         const int teams = n == 4096 ? 1 : 4;
+        // (depends on T only, like chunk_segs above: the same row means alone and inside a batch)
         e->n_chunks = std::min(296, (e->T + teams - 1) / teams);
         e->chunk_segs = (e->T + e->n_chunks - 1) / e->n_chunks;      // informational
     }
-    if (const char* mr = std::getenv("RT_V7_MAXR")) e->v7_maxr = std::atoi(mr);   // 0: launch-bounds variant (default), 112, 104, 96 (5 CTAs per SM)
-    {
-        const char* ppl = std::getenv("RT_PROBE_PLANE");
-        const char* lay = std::getenv("RT_S_LAYOUT");                 // "perm": row-major S of the register kernel (before session 5)
-        const bool can = e->reg256 && !e->tc256 && !(ppl && ppl[0] == '1') && e->v7_maxr <= 0;
-        e->t64 = !can || !lay ? 0 : (lay[0] == '8' ? 8 : (lay[0] == '3' ? 32 : 0));        // "8", "32"; default row-major (measured)
-    }
-    e->s_stride = e->tc256 ? (size_t)((e->T + 31) / 32) * 8192 : e->t64 ? (size_t)((e->T + 63) / 64) * 16384 : (size_t)e->T * n;
+    e->s_stride = e->tc256 ? (size_t)((e->T + 31) / 32) * 8192 : (size_t)e->T * n;
+    const size_t max_work = (size_t)e->n_units * n * e->n_probes;    // every probe cell a hit: the work list cannot overflow
+    // every record belongs to a different probe hit, so max_work records is the worst case; capped at 4 Mi (160 MB per slot)
+    e->max_records = cfg->max_records > 0 ? cfg->max_records : (int)std::min<size_t>(max_work, (size_t)4 << 20);
 
 #define CUE(call)                                                                                  \
     do {                                                                                           \
@@ -894,18 +893,18 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     const double amp = std::sqrt(1.0 / (cfg->sample_rate * sw2)) / 127.5;
     std::vector<float> hwin(n);
     for (int i = 0; i < n; ++i) hwin[i] = (float)(cfg->window[i] * amp);
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->dev) != cudaSuccess || sms < 1) sms = 148;
     if (e->tc256) {
         e->tc_tab = rt::tc_make_tables(cfg->window, amp);
         if (!e->tc_tab.eligible) { free_engine(e); return fail(RT_ERR_INVALID, "RT_FFT_TC256 needs a window whose DFT is confined to the bins 0 and +-1 (boxcar, hann, hamming)"); }
         e->pscale = e->tc_tab.pscale;
-        int sms = 0;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->dev) != cudaSuccess || sms < 1) sms = 148;
         constexpr int NG = 2;
         e->tc_bps = (e->T + rt::Tc256<NG>::BATCH - 1) / rt::Tc256<NG>::BATCH;
-        const long long Btot = (long long)e->n_streams * e->tc_bps;
+        const long long Btot = (long long)e->n_units * e->tc_bps;
         e->tc_grid = (int)std::max<long long>(1, std::min<long long>(sms, Btot / NG));
         const long long G = (long long)e->tc_grid * NG;
-        for (int s = 0; s < e->n_streams; ++s)
+        for (int s = 0; s < e->n_units; ++s)
             e->tc_slots = std::max(e->tc_slots, rt::tc_last_run(s, e->tc_bps, G, Btot) - rt::tc_first_run(s, e->tc_bps, G, Btot) + 1);
     }
     std::vector<float2> htw(n);
@@ -913,97 +912,73 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
         const double ang = -2.0 * M_PI * (double)k / (double)n;
         htw[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
     }
-    std::vector<float> hthr(e->n_streams);
-    for (int s = 0; s < e->n_streams; ++s) hthr[s] = (float)cfg->signal_threshold[s] * e->pscale;   // pscale is a power of two: exact
+    std::vector<float> hthr(e->n_units);
+    for (int u = 0; u < e->n_units; ++u) hthr[u] = (float)cfg->signal_threshold[u / bpl] * e->pscale;   // pscale is a power of two: exact
 
-    const size_t cells = (size_t)e->n_streams * e->s_stride;
+    const size_t cells = (size_t)e->n_units * e->s_stride;
     const size_t part_rows = e->tc256 ? (size_t)e->tc_slots : (size_t)e->n_chunks;
-    const size_t max_work = (size_t)e->n_streams * n * e->n_probes;
     CUE(cudaMalloc(&e->d_win, n * sizeof(float)));
     CUE(cudaMalloc(&e->d_tw, n * sizeof(float2)));
     for (int k = 0; k < RT_SBUFS; ++k) CUE(cudaMalloc(&e->d_S[k], cells * sizeof(float)));
-    for (int k = 0; k < 2; ++k) {
-        CUE(cudaMalloc(&e->d_part[k], (size_t)e->n_streams * part_rows * n * sizeof(float)));
-        CUE(cudaMemset(e->d_part[k], 0, (size_t)e->n_streams * part_rows * n * sizeof(float)));
+    for (int k = 0; k < RT_SLOTS; ++k) {
+        CUE(cudaMalloc(&e->d_part[k], (size_t)e->n_units * part_rows * n * sizeof(float)));
+        CUE(cudaMemset(e->d_part[k], 0, (size_t)e->n_units * part_rows * n * sizeof(float)));
+        CUE(cudaMalloc(&e->d_avg[k], (size_t)e->n_units * n * sizeof(float)));
+        CUE(cudaMalloc(&e->d_ctr[k], e->n_units * sizeof(unsigned)));
+        CUE(cudaMemset(e->d_ctr[k], 0, e->n_units * sizeof(unsigned)));
+        CUE(cudaMalloc(&e->d_rec[k], (size_t)e->max_records * sizeof(rt_record)));
+        CUE(cudaEventCreateWithFlags(&e->done[k], cudaEventDisableTiming));
+        CUE(cudaEventCreateWithFlags(&e->spec_done[k], cudaEventDisableTiming));
     }
     if (e->tc256) {
         CUE(cudaMalloc(&e->d_bmat, e->tc_tab.bmat.size() * sizeof(uint16_t)));
         CUE(cudaMemcpy(e->d_bmat, e->tc_tab.bmat.data(), e->tc_tab.bmat.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
         CUE(cudaFuncSetAttribute(rt::spectro_tc256_k<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::Tc256<2>::SMEM));
     }
-    for (int k = 0; k < 2; ++k) CUE(cudaMalloc(&e->d_avg[k], (size_t)e->n_streams * n * sizeof(float)));
-    {
-        // opt-in ("1"): measured 1 % slower per step than probing S itself (profiles/r01_scan_schedule_experiments.txt) --
-        // the probe kernel is bound by its dependent round trips, not by the sector traffic of its first one
-        const char* pp = std::getenv("RT_PROBE_PLANE");
-        if (e->reg256 && !e->tc256 && pp && pp[0] == '1')
-            for (int k = 0; k < 2; ++k) CUE(cudaMalloc(&e->d_probe[k], (size_t)e->n_streams * e->n_probes * n * sizeof(float)));
-    }
-    CUE(cudaMalloc(&e->d_ctr, e->n_streams * sizeof(unsigned)));
-    CUE(cudaMemset(e->d_ctr, 0, e->n_streams * sizeof(unsigned)));
-    CUE(cudaMalloc(&e->d_thr, e->n_streams * sizeof(float)));
-    CUE(cudaMalloc(&e->d_hasprev, e->n_streams * sizeof(int)));
+    CUE(cudaMalloc(&e->d_thr, e->n_units * sizeof(float)));
+    CUE(cudaMalloc(&e->d_hasprev, e->n_units * sizeof(int)));
     CUE(cudaMalloc(&e->d_work, max_work * sizeof(uint2)));
     CUE(cudaMalloc(&e->d_counters, 2 * RT_SLOTS * sizeof(int)));
-    for (int k = 0; k < RT_SLOTS; ++k) {
-        CUE(cudaMalloc(&e->d_rec[k], (size_t)cfg->max_records * sizeof(rt_record)));
-        CUE(cudaEventCreateWithFlags(&e->done[k], cudaEventDisableTiming));
-        CUE(cudaEventCreateWithFlags(&e->spec_done[k], cudaEventDisableTiming));
-    }
     CUE(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-    const char* ov = std::getenv("RT_SCAN_OVERLAP");     // "0": run the scan kernels on the launch stream (no overlap)
-    if (!(ov && ov[0] == '0')) {
+
+    // ---- schedule (rt_config.scan_schedule / launch_streams)
+    int sched = cfg->scan_schedule;
+    if (sched == RT_SCAN_AUTO)
+        // lean only where it was measured to win: the register kernel (the tensor-core kernel owns its SMs) with at least
+        // ~100 us of spectrogram per launch (short launches: the slower lean kernels become the critical path)
+        sched = (e->reg256 && !e->tc256 && (long long)e->n_units * e->T >= 300000) ? RT_SCAN_LEAN : RT_SCAN_OVERLAP;
+    if (sched != RT_SCAN_SERIAL) {
         // the scan kernels are small and latency bound: give them priority over the next launch's spectrogram CTAs
         int prio_lo = 0, prio_hi = 0;
         CUE(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        const char* pr = std::getenv("RT_SCAN_PRIO");                 // experiment: "lo" = same (lowest) priority as the launch stream
-        CUE(cudaStreamCreateWithPriority(&e->scan_stream, cudaStreamNonBlocking, (pr && pr[0] == 'l') ? prio_lo : prio_hi));
-    }
-    if (e->scan_stream) {
-        const char* ls = std::getenv("RT_LAUNCH_STREAMS");
-        if (!(ls && ls[0] == '1')) {
+        CUE(cudaStreamCreateWithPriority(&e->scan_stream, cudaStreamNonBlocking, prio_hi));
+        if (cfg->launch_streams != 1) {
             for (auto& q : e->lstream) CUE(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
             CUE(cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming));
             e->n_lstreams = 2;
         }
     }
-    {   // (lean kernels also run on the launch stream under RT_SCAN_OVERLAP=0: stand-alone timing of the same code)
-        // Scan kernels of the two-stream schedule: 128-thread CTAs capped at 32 registers (4096 per CTA -- what four resident
-        // spectrogram CTAs leave free on an SM), 12 per SM (8 ... 16 time the same within 1 %).  Measured 243.8 vs 255.7 us per step against the full-size scan
-        // kernels on the scan stream (profiles/r01_scan_schedule_experiments.txt).  RT_SCAN_LEAN=k: k CTAs per SM, 0: full-size.
-        const char* ln = std::getenv("RT_SCAN_LEAN");
-        int per_sm = e->scan_stream ? 12 : 0;
-        if (ln) per_sm = std::atoi(ln);
-        int sms = 0;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->dev) != cudaSuccess || sms < 1) sms = 148;
-        // default: only where it was measured to win -- the register kernel (the tensor-core kernel owns its SMs) with at least
-        // ~100 us of spectrogram per launch (short launches: the slower lean kernels become the critical path)
-        if (!ln && !(e->reg256 && !e->tc256 && (long long)e->n_streams * e->T >= 300000)) per_sm = 0;
-        if (const char* lx = std::getenv("RT_LEAN_EX")) { const int v = std::atoi(lx); if (v == 10 || v == 20 || v == 22) e->lean_ex = v; }
-        e->scan_lean = per_sm >= 1 && per_sm <= 16;
-        e->lean_ctas = sms * std::max(1, per_sm);
-        if (e->scan_lean && !std::getenv("RT_LEAN_NO_CARVEOUT")) {
-            // same shared-memory carve-out as the resident spectrogram CTAs: an SM does not change its L1 / shared split
-            // while CTAs are resident, so a kernel asking for another split could not join them
-            CUE(cudaFuncSetAttribute(probe_lean_kernel<LAYOUT_PERM>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            CUE(cudaFuncSetAttribute(probe_lean_kernel<LAYOUT_PERM64>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            CUE(cudaFuncSetAttribute(extract_kernel<LAYOUT_PERM64, 16, 2, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            CUE(cudaFuncSetAttribute(probe_lean_kernel<LAYOUT_PERM64W>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            CUE(cudaFuncSetAttribute(extract_kernel<LAYOUT_PERM64W, 16, 2, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            CUE(cudaFuncSetAttribute(probe_lean_kernel<LAYOUT_LINEAR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            CUE(cudaFuncSetAttribute(probe_lean_kernel<LAYOUT_TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            CUE(cudaFuncSetAttribute(extract_kernel<LAYOUT_PERM, 16, 2, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            CUE(cudaFuncSetAttribute(extract_kernel<LAYOUT_LINEAR, 16, 2, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            CUE(cudaFuncSetAttribute(extract_kernel<LAYOUT_TILE, 16, 2, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            CUE(cudaFuncSetAttribute(row_mean_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        }
+    e->scan_lean = sched == RT_SCAN_LEAN;
+    // lean scan kernels: 128-thread CTAs capped at 32 registers (4096 per CTA -- what four resident spectrogram CTAs leave free
+    // on an SM), 12 per SM (8 ... 16 time the same within 1 %)
+    e->lean_ctas = sms * 12;
+    if (e->scan_lean) {
+        // same shared-memory carve-out as the resident spectrogram CTAs: an SM does not change its L1 / shared split
+        // while CTAs are resident, so a kernel asking for another split could not join them
+        CUE(cudaFuncSetAttribute(row_mean_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CUE(cudaFuncSetAttribute(probe_lean_kernel<LAYOUT_PERM>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CUE(cudaFuncSetAttribute(probe_lean_kernel<LAYOUT_LINEAR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CUE(cudaFuncSetAttribute(probe_lean_kernel<LAYOUT_TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CUE(cudaFuncSetAttribute(extract_kernel<LAYOUT_PERM, 16, 1, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CUE(cudaFuncSetAttribute(extract_kernel<LAYOUT_LINEAR, 16, 1, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CUE(cudaFuncSetAttribute(extract_kernel<LAYOUT_TILE, 16, 1, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     }
-    CUE(cudaMallocHost(&e->h_rec, (size_t)cfg->max_records * sizeof(rt_record)));
     CUE(cudaMallocHost(&e->h_counters, 2 * sizeof(int)));
     CUE(cudaMemcpy(e->d_win, hwin.data(), n * sizeof(float), cudaMemcpyHostToDevice));
     CUE(cudaMemcpy(e->d_tw, htw.data(), n * sizeof(float2), cudaMemcpyHostToDevice));
-    CUE(cudaMemcpy(e->d_thr, hthr.data(), e->n_streams * sizeof(float), cudaMemcpyHostToDevice));
+    CUE(cudaMemcpy(e->d_thr, hthr.data(), e->n_units * sizeof(float), cudaMemcpyHostToDevice));
     e->h_hasprev.assign(e->n_streams, 0);
+    e->h_hasprev_units.assign(e->n_units, 0);
     e->hasprev_dirty = true;
     if (e->r16) {
         if (n == 4096) CUE(cudaFuncSetAttribute(rt::spectro_r16_k<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R16Cfg<4096>::SMEM));
@@ -1013,30 +988,8 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
         const size_t smem = (size_t)n * (2 * sizeof(float2) + sizeof(float)) + 16;
         CUE(cudaFuncSetAttribute(spectro_generic<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     } else {
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7t<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7t<true, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7t<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7t<true, 32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7x<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7x<true, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7x<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7x<true, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7x<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7x<true, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7h<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7h<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7n<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7n<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7p<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7p<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7r<true, 112>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7r<true, 112>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7r<true, 104>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7r<true, 104>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7r<true, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7r<true, 96>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     }
 #undef CUE
     *out = e;
@@ -1049,6 +1002,7 @@ int rt_engine_set_stream(rt_engine* e, void* cuda_stream) {
     if (!e) return fail(RT_ERR_INVALID, "null engine");
     CU(cudaSetDevice(e->dev));
     CU(cudaStreamSynchronize(e->stream));
+    for (auto& ls : e->lstream) if (ls) CU(cudaStreamSynchronize(ls));
     if (e->scan_stream) CU(cudaStreamSynchronize(e->scan_stream));
     if (e->own_stream) {
         CU(cudaStreamDestroy(e->stream));
@@ -1067,7 +1021,7 @@ int rt_engine_reset_stream(rt_engine* e, int32_t stream) {
 
 int rt_engine_shape(const rt_engine* e, int32_t* n_streams, int32_t* nperseg, int32_t* T) {
     if (!e) return fail(RT_ERR_INVALID, "null engine");
-    if (n_streams) *n_streams = e->n_streams;
+    if (n_streams) *n_streams = e->n_units;
     if (nperseg) *nperseg = e->n;
     if (T) *T = e->T;
     return RT_OK;
@@ -1075,8 +1029,8 @@ int rt_engine_shape(const rt_engine* e, int32_t* n_streams, int32_t* nperseg, in
 
 int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size_t stream_stride_bytes) {
     if (!e || !iq) return fail(RT_ERR_INVALID, "null argument");
-    const size_t block_bytes = 2 * (size_t)e->cfg.block_samples;
-    if (stream_stride_bytes < block_bytes && e->n_streams > 1) return fail(RT_ERR_INVALID, "stream_stride_bytes smaller than one block");
+    const size_t stream_bytes = e->block_bytes * (size_t)e->bpl;     // the consecutive blocks of one stream
+    if (stream_stride_bytes < stream_bytes && e->n_streams > 1) return fail(RT_ERR_INVALID, "stream_stride_bytes smaller than one stream's blocks");
     CU(cudaSetDevice(e->dev));
     cudaStream_t st = e->stream;
     if (e->n_lstreams == 2) {
@@ -1089,7 +1043,7 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     size_t stride = stream_stride_bytes;
     if (!iq_on_device) {
         if (!e->d_stage[0]) {
-            e->stage_stride = (block_bytes + 255) & ~(size_t)255;
+            e->stage_stride = (stream_bytes + 255) & ~(size_t)255;
             for (int k = 0; k < 2; ++k) {
                 CU(cudaMalloc(&e->d_stage[k], e->stage_stride * e->n_streams));
                 CU(cudaEventCreateWithFlags(&e->h2d_done[k], cudaEventDisableTiming));
@@ -1100,17 +1054,19 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
         const int sb = (int)(e->h2d_seq & 1);
         if (e->h2d_seq >= 2) CU(cudaStreamWaitEvent(e->h2d_stream, e->stage_free[sb], 0));   // the spectrogram kernel that read this buffer is done
         if (e->stage_stride == stream_stride_bytes || e->n_streams == 1)    // packed batch: one linear DMA instead of n_streams row copies
-            CU(cudaMemcpyAsync(e->d_stage[sb], iq, e->n_streams == 1 ? block_bytes : e->stage_stride * e->n_streams, cudaMemcpyHostToDevice, e->h2d_stream));
+            CU(cudaMemcpyAsync(e->d_stage[sb], iq, e->n_streams == 1 ? stream_bytes : e->stage_stride * e->n_streams, cudaMemcpyHostToDevice, e->h2d_stream));
         else
-            CU(cudaMemcpy2DAsync(e->d_stage[sb], e->stage_stride, iq, stream_stride_bytes, block_bytes, e->n_streams,
+            CU(cudaMemcpy2DAsync(e->d_stage[sb], e->stage_stride, iq, stream_stride_bytes, stream_bytes, e->n_streams,
                                  cudaMemcpyHostToDevice, e->h2d_stream));
         CU(cudaEventRecord(e->h2d_done[sb], e->h2d_stream));
         CU(cudaStreamWaitEvent(st, e->h2d_done[sb], 0));
         d_iq = e->d_stage[sb];
         stride = e->stage_stride;
     }
+    const bool aligned = (((uintptr_t)d_iq | stride | (e->bpl > 1 ? e->block_bytes : 0)) & 15) == 0;
+    if (e->reg256 && !aligned) return fail(RT_ERR_INVALID, "register FFT path needs 16-byte aligned IQ, stream stride and (blocks_per_launch > 1) block size");
     const int slot = (int)(e->launch_seq % RT_SLOTS);
-    if (e->launch_seq - e->fetch_seq == RT_SLOTS) e->fetch_seq++;      // ring full: the oldest unfetched result is dropped
+    if (e->launch_seq - e->fetch_seq == RT_SLOTS) { e->fetch_seq++; e->peeked = false; }   // ring full: the oldest unfetched result is dropped
     int* d_cnt = e->d_counters + 2 * slot;
     cudaStream_t sc_st = e->scan_stream ? e->scan_stream : st;
     // Two streams: the spectrogram of this launch runs on the launch stream while the scan kernels of the
@@ -1119,8 +1075,8 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     if (e->launch_seq >= RT_SLOTS && e->scan_stream) CU(cudaStreamWaitEvent(st, e->done[slot], 0));
 
     rt_engine::EvSet* evs = nullptr;
-    if (e->timing) e->timing_launches++;
-    if (e->timing && ((e->timing_launches - 1) % e->timing_period) == 0) {
+    if (e->timing_period > 0) e->timing_launches++;
+    if (e->timing_period > 0 && ((e->timing_launches - 1) % e->timing_period) == 0) {
         e->timed_launches++;
         if (e->ev_used == e->ev_pool.size()) {
             if (e->ev_pool.size() >= 4096) { int rc = harvest_timing(e); if (rc) return rc; }
@@ -1137,36 +1093,23 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     const int next = (e->cur + 1) % RT_SBUFS;
     SpectroArgs sa;
     sa.iq = d_iq; sa.stream_stride = stride; sa.n = e->n; sa.T = e->T;
+    sa.bpl = e->bpl; sa.block_bytes = e->block_bytes;
     sa.chunk_segs = e->chunk_segs; sa.n_chunks = e->n_chunks;
     sa.win = e->d_win; sa.tw = e->d_tw; sa.S = e->d_S[next]; sa.part = e->d_part[slot];
     sa.S_stream_stride = e->s_stride;
-    sa.probe = e->d_probe[slot]; sa.probe_stride = e->cfg.probe_stride; sa.n_probes = e->n_probes;
-    const bool aligned = (((uintptr_t)d_iq | stride) & 15) == 0;
-    const bool use_reg = e->reg256 && aligned;
-    if (e->reg256 && !aligned) return fail(RT_ERR_INVALID, "register FFT path needs 16-byte aligned IQ and stream stride");
-    dim3 grid(e->n_chunks, e->n_streams);
+    const bool use_reg = e->reg256;
+    dim3 grid(e->n_chunks, e->n_units);
     if (use_reg && e->tc256) {
         rt::TcArgs ta;
-        ta.iq = d_iq; ta.stream_stride = stride; ta.T = e->T; ta.n_streams = e->n_streams;
-        ta.bps = e->tc_bps; ta.total_batches = e->n_streams * e->tc_bps;
+        ta.iq = d_iq; ta.stream_stride = stride; ta.T = e->T; ta.n_streams = e->n_units;
+        ta.bps = e->tc_bps; ta.total_batches = e->n_units * e->tc_bps;
         ta.bmat = e->d_bmat; ta.wc0 = e->tc_tab.wc0; ta.wc1 = e->tc_tab.wc1; ta.wc255 = e->tc_tab.wc255;
         ta.S = e->d_S[next]; ta.S_stream_stride = e->s_stride;
-        ta.part = e->d_part[slot]; ta.part_slots = e->tc_slots; ta.avg = e->d_avg[slot]; ta.ctr = e->d_ctr;
+        ta.part = e->d_part[slot]; ta.part_slots = e->tc_slots; ta.avg = e->d_avg[slot]; ta.ctr = e->d_ctr[slot];
         ta.store = 1; ta.dbg = 0; ta.prof = nullptr;
         rt::spectro_tc256_k<2><<<e->tc_grid, 512, rt::Tc256<2>::SMEM, st>>>(ta);
     } else if (use_reg) {
-        if (e->t64 == 8) rt::spectro_reg256_v7t<true, 8><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
-        else if (e->t64 == 32) rt::spectro_reg256_v7t<true, 32><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
-        else if (e->d_probe[slot]) rt::spectro_reg256_v7p<true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
-        else if (e->v7_maxr == 112) rt::spectro_reg256_v7r<true, 112><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
-        else if (e->v7_maxr == 104) rt::spectro_reg256_v7r<true, 104><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
-        else if (e->v7_maxr == 96) rt::spectro_reg256_v7r<true, 96><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
-        else if (e->v7_maxr == -5) rt::spectro_reg256_v7h<true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
-        else if (e->v7_maxr == -2) rt::spectro_reg256_v7x<true, true, false><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
-        else if (e->v7_maxr == -3) rt::spectro_reg256_v7x<true, false, true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
-        else if (e->v7_maxr == -4) rt::spectro_reg256_v7x<true, true, true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
-        else if (e->v7_maxr == -1) rt::spectro_reg256_v7n<true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);   // RT_V7_MAXR=-1: pinned addresses
-        else rt::spectro_reg256_v7<true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
+        rt::spectro_reg256_v7n<true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
     } else if (e->r16 && aligned) {
         if (e->n == 4096) rt::spectro_r16_k<4096><<<grid, 256, rt::R16Cfg<4096>::SMEM, st>>>(sa);
         else rt::spectro_r16_k<1024><<<grid, 256, rt::R16Cfg<1024>::SMEM, st>>>(sa);
@@ -1182,78 +1125,56 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     // ---- scan stream: probe, extraction (in launch order; d_work / d_hasprev live here)
     if (e->scan_stream) CU(cudaStreamWaitEvent(sc_st, e->spec_done[slot], 0));
     if (e->hasprev_dirty) {
-        CU(cudaMemcpyAsync(e->d_hasprev, e->h_hasprev.data(), e->n_streams * sizeof(int), cudaMemcpyHostToDevice, sc_st));
+        for (int u = 0; u < e->n_units; ++u) e->h_hasprev_units[u] = (u % e->bpl) ? 1 : e->h_hasprev[u / e->bpl];
+        // pageable source: the driver stages it before returning, so the vector may change right after
+        CU(cudaMemcpyAsync(e->d_hasprev, e->h_hasprev_units.data(), e->n_units * sizeof(int), cudaMemcpyHostToDevice, sc_st));
         e->hasprev_dirty = false;
     }
     CU(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), sc_st));
     if (evs) CU(cudaEventRecord(evs->ev[2], sc_st));
     const bool lean = e->scan_lean;
+    // the r16 kernel leaves one partial row per CTA: its n_chunks is the number of partial rows per unit either way
     const bool sep_mean = !(use_reg && e->tc256) && (lean || e->n_chunks > 48);
     if (sep_mean) {
-        row_mean_kernel<<<dim3((4 * e->n + 127) / 128, e->n_streams), 128, 0, sc_st>>>(e->d_part[slot], e->d_avg[slot], e->n, e->n_chunks, e->T, (use_reg && !e->tc256) ? 1 : 0);
+        row_mean_kernel<<<dim3((4 * e->n + 127) / 128, e->n_units), 128, 0, sc_st>>>(e->d_part[slot], e->d_avg[slot], e->n, e->n_chunks, e->T, (use_reg && !e->tc256) ? 1 : 0);
         CU(cudaGetLastError());
     }
     if (evs) CU(cudaEventRecord(evs->ev[3], sc_st));
 
     ScanArgs sc;
-    sc.S = e->d_S[next]; sc.Sprev = e->d_S[e->cur]; sc.P = (use_reg && !e->tc256) ? e->d_probe[slot] : nullptr; sc.stream_stride = e->s_stride; sc.avg = e->d_avg[slot]; sc.part = ((use_reg && e->tc256) || sep_mean) ? nullptr : e->d_part[slot]; sc.n_chunks = e->n_chunks; sc.part_perm = (use_reg && !e->tc256) ? 1 : 0; sc.thr = e->d_thr; sc.has_prev = e->d_hasprev;
-    // timing experiment only (results are wrong): every stream's scan reads stream 0's spectrogram, i.e. a 19 MB region that stays
-    // in L2 -- the same instructions without the scattered DRAM reads (profiles/r01_scan_schedule_experiments.txt)
-    if (std::getenv("RT_SCAN_EXPERIMENT_L2")) sc.stream_stride = 0;
+    sc.S = e->d_S[next]; sc.Sprev = e->d_S[e->cur]; sc.stream_stride = e->s_stride; sc.avg = e->d_avg[slot];
+    sc.part = ((use_reg && e->tc256) || sep_mean) ? nullptr : e->d_part[slot];
+    sc.n_chunks = e->n_chunks; sc.part_perm = (use_reg && !e->tc256) ? 1 : 0; sc.thr = e->d_thr; sc.has_prev = e->d_hasprev;
+    sc.bpl = e->bpl;
     sc.snr = (float)e->cfg.snr_threshold;
     sc.n = e->n; sc.T = e->T; sc.stride = e->cfg.probe_stride; sc.n_probes = e->n_probes;
     sc.min_cols = e->cfg.min_cols; sc.max_cols = e->cfg.max_cols;
-    sc.n_streams_scan = e->n_streams;
-    sc.work = e->d_work; sc.counters = d_cnt; sc.rec = e->d_rec[slot]; sc.max_records = e->cfg.max_records;
-    const int pth = e->probe_threads, eth = e->extract_threads, ect = e->extract_ctas;
-    const int pbins = std::min(e->n, pth);
+    sc.n_streams_scan = e->n_units;
+    sc.work = e->d_work; sc.counters = d_cnt; sc.rec = e->d_rec[slot]; sc.max_records = e->max_records;
+    const int pbins = std::min(e->n, 256);
     const int ppt = e->probe_ppt;
-    dim3 pgrid(((e->n + pbins - 1) / pbins) * ((e->n_probes + ppt - 1) / ppt), e->n_streams);
+    dim3 pgrid(((e->n + pbins - 1) / pbins) * ((e->n_probes + ppt - 1) / ppt), e->n_units);
 #define RT_PROBE(L)                                                                        \
     do {                                                                                   \
-        if (ppt == 8) probe_kernel<L, 8><<<pgrid, pbins, 0, sc_st>>>(sc);                  \
+        if (lean) probe_lean_kernel<L><<<e->lean_ctas, 128, 0, sc_st>>>(sc);               \
+        else if (ppt == 8) probe_kernel<L, 8><<<pgrid, pbins, 0, sc_st>>>(sc);             \
         else if (ppt == 16) probe_kernel<L, 16><<<pgrid, pbins, 0, sc_st>>>(sc);           \
         else probe_kernel<L, 32><<<pgrid, pbins, 0, sc_st>>>(sc);                          \
     } while (0)
-    if (lean) {
-        if (use_reg && e->tc256) probe_lean_kernel<LAYOUT_TILE><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
-        else if (use_reg && e->t64 == 8) probe_lean_kernel<LAYOUT_PERM64><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
-        else if (use_reg && e->t64 == 32) probe_lean_kernel<LAYOUT_PERM64W><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
-        else if (use_reg) probe_lean_kernel<LAYOUT_PERM><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
-        else probe_lean_kernel<LAYOUT_LINEAR><<<e->lean_ctas, 128, 0, sc_st>>>(sc);
-    }
-    else if (use_reg && e->tc256) RT_PROBE(LAYOUT_TILE);
-    else if (use_reg && e->t64 == 8) RT_PROBE(LAYOUT_PERM64);
-    else if (use_reg && e->t64 == 32) RT_PROBE(LAYOUT_PERM64W);
+    if (use_reg && e->tc256) RT_PROBE(LAYOUT_TILE);
     else if (use_reg) RT_PROBE(LAYOUT_PERM);
     else RT_PROBE(LAYOUT_LINEAR);
 #undef RT_PROBE
     CU(cudaGetLastError());
     if (evs) CU(cudaEventRecord(evs->ev[4], sc_st));
-    const int emb = eth == 128 ? e->extract_minb : 0;
+    // full size: one wave of 128-thread CTAs, four 32-cell windows per round trip; lean: one 32-cell window, no speculative
+    // forward fetch (fewest sectors: the kernel runs beside the spectrogram of the next launch)
 #define RT_EXTRACT(L)                                                                      \
     do {                                                                                   \
-        if (emb == 16) extract_kernel<L, 16><<<ect, eth, 0, sc_st>>>(sc);                  \
-        else if (emb == 12) extract_kernel<L, 12><<<ect, eth, 0, sc_st>>>(sc);             \
-        else extract_kernel<L, 0><<<ect, eth, 0, sc_st>>>(sc);                             \
+        if (lean) extract_kernel<L, 16, 1, 0><<<e->lean_ctas, 128, 0, sc_st>>>(sc);        \
+        else extract_kernel<L, 0><<<148 * 24, 128, 0, sc_st>>>(sc);                        \
     } while (0)
-    if (lean) {
-#define RT_LEAN_EXTRACT(L)                                                                                          \
-    do {                                                                                                            \
-        if (e->lean_ex == 10) extract_kernel<L, 16, 1, 0><<<e->lean_ctas, 128, 0, sc_st>>>(sc);                     \
-        else if (e->lean_ex == 20) extract_kernel<L, 16, 2, 0><<<e->lean_ctas, 128, 0, sc_st>>>(sc);                \
-        else extract_kernel<L, 16, 2, 2><<<e->lean_ctas, 128, 0, sc_st>>>(sc);                                      \
-    } while (0)
-        if (use_reg && e->tc256) RT_LEAN_EXTRACT(LAYOUT_TILE);
-        else if (use_reg && e->t64 == 8) RT_LEAN_EXTRACT(LAYOUT_PERM64);
-        else if (use_reg && e->t64 == 32) RT_LEAN_EXTRACT(LAYOUT_PERM64W);
-        else if (use_reg) RT_LEAN_EXTRACT(LAYOUT_PERM);
-        else RT_LEAN_EXTRACT(LAYOUT_LINEAR);
-#undef RT_LEAN_EXTRACT
-    }
-    else if (use_reg && e->tc256) RT_EXTRACT(LAYOUT_TILE);
-    else if (use_reg && e->t64 == 8) RT_EXTRACT(LAYOUT_PERM64);
-    else if (use_reg && e->t64 == 32) RT_EXTRACT(LAYOUT_PERM64W);
+    if (use_reg && e->tc256) RT_EXTRACT(LAYOUT_TILE);
     else if (use_reg) RT_EXTRACT(LAYOUT_PERM);
     else RT_EXTRACT(LAYOUT_LINEAR);
 #undef RT_EXTRACT
@@ -1271,40 +1192,56 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     return RT_OK;
 }
 
+int rt_engine_peek(rt_engine* e, int32_t* n_records) {
+    if (!e || !n_records) return fail(RT_ERR_INVALID, "null argument");
+    if (e->fetch_seq == e->launch_seq) return fail(RT_ERR_STATE, "rt_engine_peek without an unfetched rt_engine_launch");
+    CU(cudaSetDevice(e->dev));
+    int rc = peek_oldest(e);
+    if (rc) return rc;
+    *n_records = std::min(e->h_counters[1], e->max_records);
+    return RT_OK;
+}
+
 int rt_engine_fetch(rt_engine* e, rt_record* out, int32_t max_out, int32_t* n_out) {
     if (!e || !n_out) return fail(RT_ERR_INVALID, "null argument");
     if (e->fetch_seq == e->launch_seq) return fail(RT_ERR_STATE, "rt_engine_fetch without an unfetched rt_engine_launch");
     CU(cudaSetDevice(e->dev));
+    int rc = peek_oldest(e);
+    if (rc) return rc;
     const int slot = (int)(e->fetch_seq % RT_SLOTS);
     e->fetch_seq++;
-    // copy on a side stream that only waits for THIS launch, so a later launch already queued does not delay it
-    CU(cudaStreamWaitEvent(e->copy_stream, e->done[slot], 0));
-    CU(cudaMemcpyAsync(e->h_counters, e->d_counters + 2 * slot, 2 * sizeof(int), cudaMemcpyDeviceToHost, e->copy_stream));
-    CU(cudaStreamSynchronize(e->copy_stream));
+    e->peeked = false;
     const int nrec = e->h_counters[1];
     e->last_work_items = e->h_counters[0];
     e->last_records = nrec;
     *n_out = nrec;
-    if (nrec > e->cfg.max_records) return fail(RT_ERR_OVERFLOW, "more candidate records than rt_config.max_records");
-    if (nrec > max_out || (nrec > 0 && !out)) return fail(RT_ERR_OVERFLOW, "output buffer smaller than the number of records");
-    if (nrec > 0) {
-        CU(cudaMemcpyAsync(e->h_rec, e->d_rec[slot], (size_t)nrec * sizeof(rt_record), cudaMemcpyDeviceToHost, e->copy_stream));
+    const int have = std::max(0, std::min(nrec, std::min(e->max_records, out ? max_out : 0)));
+    if (have > 0) {
+        if ((size_t)have > e->h_rec_cap) {
+            if (e->h_rec) CU(cudaFreeHost(e->h_rec));
+            e->h_rec = nullptr;
+            e->h_rec_cap = std::max<size_t>((size_t)have + have / 2, 4096);
+            CU(cudaMallocHost(&e->h_rec, e->h_rec_cap * sizeof(rt_record)));
+        }
+        CU(cudaMemcpyAsync(e->h_rec, e->d_rec[slot], (size_t)have * sizeof(rt_record), cudaMemcpyDeviceToHost, e->copy_stream));
         CU(cudaStreamSynchronize(e->copy_stream));
-        std::sort(e->h_rec, e->h_rec + nrec, [](const rt_record& x, const rt_record& y) {
+        std::sort(e->h_rec, e->h_rec + have, [](const rt_record& x, const rt_record& y) {
             if (x.stream != y.stream) return x.stream < y.stream;
             if (x.fi != y.fi) return x.fi < y.fi;
             return x.start < y.start;
         });
         if (e->pscale != 1.f) {
             const float inv = 1.f / e->pscale;           // power of two: exact
-            for (int i = 0; i < nrec; ++i) {
+            for (int i = 0; i < have; ++i) {
                 e->h_rec[i].max_lin *= inv;
                 e->h_rec[i].row_mean *= inv;
                 e->h_rec[i].mean_lin *= (double)inv;
             }
         }
-        std::memcpy(out, e->h_rec, (size_t)nrec * sizeof(rt_record));
+        std::memcpy(out, e->h_rec, (size_t)have * sizeof(rt_record));
     }
+    if (nrec > e->max_records) return fail(RT_ERR_OVERFLOW, "more candidate records than rt_config.max_records (the first max_records were returned)");
+    if (nrec > have) return fail(RT_ERR_OVERFLOW, "output buffer smaller than the number of records (the first max_out were returned)");
     return RT_OK;
 }
 
@@ -1344,18 +1281,17 @@ int rt_engine_process(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, siz
 }
 
 int rt_engine_read_spectrogram(rt_engine* e, int32_t stream, float* out) {
-    if (!e || !out || stream < 0 || stream >= e->n_streams) return fail(RT_ERR_INVALID, "bad argument");
+    if (!e || !out || stream < 0 || stream >= e->n_units) return fail(RT_ERR_INVALID, "bad argument");
     if (!e->launched) return fail(RT_ERR_STATE, "no launch yet");
     CU(cudaSetDevice(e->dev));
     const size_t cells = (size_t)e->T * e->n;
     const float* src = e->d_S[e->cur] + (size_t)stream * e->s_stride;
     CU(cudaStreamSynchronize(e->stream));
+    for (auto& ls : e->lstream) if (ls) CU(cudaStreamSynchronize(ls));
     if (e->scan_stream) CU(cudaStreamSynchronize(e->scan_stream));
     if (e->reg256) {
         if (!e->d_tmp) CU(cudaMalloc(&e->d_tmp, cells * sizeof(float)));
         if (e->tc256) untile_kernel<LAYOUT_TILE><<<(unsigned)((cells + 255) / 256), 256, 0, e->stream>>>(src, e->d_tmp, (int)cells, 1.f / e->pscale);
-        else if (e->t64 == 32) untile_kernel<LAYOUT_PERM64W><<<(unsigned)((cells + 255) / 256), 256, 0, e->stream>>>(src, e->d_tmp, (int)cells, 1.f);
-        else if (e->t64 == 8) untile_kernel<LAYOUT_PERM64><<<(unsigned)((cells + 255) / 256), 256, 0, e->stream>>>(src, e->d_tmp, (int)cells, 1.f);
         else untile_kernel<LAYOUT_PERM><<<(unsigned)((cells + 255) / 256), 256, 0, e->stream>>>(src, e->d_tmp, (int)cells, 1.f);
         CU(cudaGetLastError());
         src = e->d_tmp;
@@ -1366,9 +1302,10 @@ int rt_engine_read_spectrogram(rt_engine* e, int32_t stream, float* out) {
 }
 
 int rt_engine_read_row_means(rt_engine* e, int32_t stream, float* out) {
-    if (!e || !out || stream < 0 || stream >= e->n_streams) return fail(RT_ERR_INVALID, "bad argument");
+    if (!e || !out || stream < 0 || stream >= e->n_units) return fail(RT_ERR_INVALID, "bad argument");
     if (!e->launched) return fail(RT_ERR_STATE, "no launch yet");
     CU(cudaSetDevice(e->dev));
+    for (auto& ls : e->lstream) if (ls) CU(cudaStreamSynchronize(ls));
     if (e->scan_stream) CU(cudaStreamSynchronize(e->scan_stream));      // the row means are written on the scan stream
     CU(cudaMemcpyAsync(out, e->d_avg[(int)((e->launch_seq - 1) % RT_SLOTS)] + (size_t)stream * e->n, e->n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
@@ -1377,11 +1314,10 @@ int rt_engine_read_row_means(rt_engine* e, int32_t stream, float* out) {
     return RT_OK;
 }
 
-int rt_engine_enable_timing(rt_engine* e, int32_t on) {
-    if (!e) return fail(RT_ERR_INVALID, "null engine");
-    if (!on) { int rc = harvest_timing(e); if (rc) return rc; }
-    e->timing = on != 0;
-    if (const char* tp = std::getenv("RT_TIMING_PERIOD")) { const int v = std::atoi(tp); if (v >= 1) e->timing_period = v; }
+int rt_engine_enable_timing(rt_engine* e, int32_t period) {
+    if (!e || period < 0) return fail(RT_ERR_INVALID, "null engine / negative period");
+    if (period == 0) { int rc = harvest_timing(e); if (rc) return rc; }
+    e->timing_period = period;
     return RT_OK;
 }
 

@@ -53,7 +53,7 @@ __global__ void __maxnreg__(104) spectro_r16_k(SpectroArgs a) {   // 2 CTAs/SM a
     const uint32_t bar0 = smem_u32(r16_smem + C::OFF_BAR) + team * 16;
 
     const int s = blockIdx.y;
-    const uint8_t* base = a.iq + (size_t)s * a.stream_stride;
+    const uint8_t* base = a.unit_base(s);
     // segments are dealt round-robin over the (CTA, team) pairs of the stream: one twiddle-table load per CTA,
     // balanced work for any T; this team's segments: first, first + step, ...
     const int step = a.n_chunks * C::TEAMS;

@@ -5,6 +5,7 @@ CPU fallback: if the shared library is missing or no CUDA device is present, cre
 an `Engine` raises.
 """
 import ctypes
+import logging
 import os
 from typing import Optional, Sequence, Tuple, Union
 
@@ -13,13 +14,16 @@ import numpy as np
 from . import build as _build
 
 RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_OVERFLOW, RT_ERR_STATE = 0, -1, -2, -3, -4
-RT_ABI_VERSION = 1
+RT_ABI_VERSION = 2
 FFT_AUTO, FFT_GENERIC, FFT_REG256, FFT_TC256 = 0, 1, 2, 3
+SCAN_AUTO, SCAN_SERIAL, SCAN_OVERLAP, SCAN_LEAN = 0, 1, 2, 3
+
+logger = logging.getLogger(__name__)
 
 # every symbol include/rt_engine.h declares
 EXPORTS = (
     "rt_last_error", "rt_abi_version", "rt_device_count", "rt_engine_create", "rt_engine_destroy",
-    "rt_engine_set_stream", "rt_engine_reset_stream", "rt_engine_process", "rt_engine_launch", "rt_engine_fetch",
+    "rt_engine_set_stream", "rt_engine_reset_stream", "rt_engine_process", "rt_engine_launch", "rt_engine_fetch", "rt_engine_peek",
     "rt_engine_shape", "rt_engine_read_spectrogram", "rt_engine_read_row_means", "rt_engine_enable_timing",
     "rt_engine_get_timing", "rt_engine_join", "rt_engine_last_counts", "rt_tc256_tables",
     # include/rt_matcher.h
@@ -35,7 +39,8 @@ class RtConfig(ctypes.Structure):
         ("window", ctypes.POINTER(ctypes.c_double)), ("signal_threshold", ctypes.POINTER(ctypes.c_double)),
         ("snr_threshold", ctypes.c_double), ("probe_stride", ctypes.c_int32), ("min_cols", ctypes.c_int32),
         ("max_cols", ctypes.c_int32), ("max_records", ctypes.c_int32), ("fft_impl", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("scan_schedule", ctypes.c_int32), ("launch_streams", ctypes.c_int32), ("chunk_segs", ctypes.c_int32),
+        ("blocks_per_launch", ctypes.c_int32), ("reserved", ctypes.c_int32 * 3),
     ]
 
 
@@ -85,6 +90,7 @@ def load_library() -> ctypes.CDLL:
                                       ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
     lib.rt_engine_launch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_size_t]
     lib.rt_engine_fetch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
+    lib.rt_engine_peek.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32)]
     lib.rt_engine_join.argtypes = [ctypes.c_void_p]
     lib.rt_tc256_tables.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.rt_engine_last_counts.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
@@ -111,19 +117,39 @@ def device_count() -> int:
     return n
 
 
-def _device_pointer(obj) -> Optional[Tuple[int, int]]:
-    """(pointer, row stride in bytes) if `obj` lives in device memory, else None."""
+def _device_pointer(obj, n_rows: int, row_bytes: int) -> Optional[Tuple[int, int]]:
+    """(pointer, row stride in bytes) if `obj` lives in device memory, else None.  `obj` must be uint8 and hold
+    `n_rows` rows of `row_bytes` contiguous bytes (a 1-D object: one row); a wrong size would be read out of bounds."""
     if hasattr(obj, "data_ptr") and getattr(obj, "is_cuda", False):      # torch.Tensor, without importing torch
-        if obj.dim() == 1:
-            return int(obj.data_ptr()), int(obj.numel() * obj.element_size())
-        return int(obj.data_ptr()), int(obj.stride(0) * obj.element_size())
-    cai = getattr(obj, "__cuda_array_interface__", None)
-    if cai is not None:
-        shape = cai["shape"]
-        strides = cai.get("strides")
-        row = strides[0] if strides else int(np.prod(shape[1:]))
-        return int(cai["data"][0]), int(row)
-    return None
+        if "uint8" not in str(obj.dtype):
+            raise TypeError("IQ blocks must be uint8 interleaved I,Q bytes")
+        shape, strides = tuple(obj.shape), tuple(int(x) for x in obj.stride())
+        ptr = int(obj.data_ptr())
+    else:
+        cai = getattr(obj, "__cuda_array_interface__", None)
+        if cai is None:
+            return None
+        if cai["typestr"] not in ("|u1", "<u1", ">u1"):
+            raise TypeError("IQ blocks must be uint8 interleaved I,Q bytes")
+        shape = tuple(cai["shape"])
+        st = cai.get("strides")
+        if st is None:                                                   # C-contiguous: strides in BYTES (itemsize 1)
+            st, acc = [], 1
+            for d in reversed(shape):
+                st.insert(0, acc)
+                acc *= d
+        strides = tuple(int(x) for x in st)
+        ptr = int(cai["data"][0])
+    # the trailing axes of a row must be dense; the leading axis is the stream
+    if len(shape) == 1:
+        shape, strides = (1,) + shape, (shape[0] * strides[0],) + strides
+    inner, dense = 1, True
+    for d, st in zip(reversed(shape[1:]), reversed(strides[1:])):
+        dense = dense and (d == 1 or st == inner)
+        inner *= d
+    if shape[0] != n_rows or inner != row_bytes or not dense:
+        raise ValueError(f"expected uint8 [{n_rows}, {row_bytes}] on the device, got shape {shape} strides {strides}")
+    return ptr, (strides[0] if n_rows > 1 else row_bytes)
 
 
 class Engine:
@@ -131,7 +157,8 @@ class Engine:
 
     def __init__(self, *, n_streams: int, block_samples: int, nperseg: int, window: np.ndarray, sample_rate: float,
                  signal_threshold: Union[float, Sequence[float]], snr_threshold: float, probe_stride: int,
-                 min_cols: int, max_cols: int, max_records: int = 1 << 16, cuda_device: int = 0, fft_impl: int = FFT_AUTO):
+                 min_cols: int, max_cols: int, max_records: int = 0, cuda_device: int = 0, fft_impl: int = FFT_AUTO,
+                 scan_schedule: int = SCAN_AUTO, launch_streams: int = 0, chunk_segs: int = 0, blocks_per_launch: int = 1):
         self._lib = load_library()
         self._h = ctypes.c_void_p()
         win = np.ascontiguousarray(window, dtype=np.float64)
@@ -144,14 +171,17 @@ class Engine:
             window=win.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
             signal_threshold=thr.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
             snr_threshold=float(snr_threshold), probe_stride=int(probe_stride), min_cols=int(min_cols),
-            max_cols=int(max_cols), max_records=int(max_records), fft_impl=int(fft_impl), reserved=0,
+            max_cols=int(max_cols), max_records=int(max_records), fft_impl=int(fft_impl),
+            scan_schedule=int(scan_schedule), launch_streams=int(launch_streams), chunk_segs=int(chunk_segs),
+            blocks_per_launch=int(blocks_per_launch),
         )
         _check(self._lib.rt_engine_create(ctypes.byref(cfg), ctypes.byref(self._h)))
         self.n_streams, self.nperseg, self.block_samples = n_streams, nperseg, block_samples
+        self.blocks_per_launch = int(blocks_per_launch)
+        self.n_units = n_streams * self.blocks_per_launch      # analyzer units per launch: rt_record.stream counts these
         self.T = block_samples // nperseg
-        self.max_records = int(max_records)
         self.cuda_device = cuda_device
-        self._out = np.empty(self.max_records, dtype=RECORD_DTYPE)
+        self.truncated = 0           # records the last fetch could not return (rt_config.max_records exceeded)
         self._keepalive = []         # host buffers of launches not fetched yet (the H2D copy is asynchronous)
 
     # -- lifetime ---------------------------------------------------------------------------
@@ -174,36 +204,48 @@ class Engine:
 
     # -- data path ----------------------------------------------------------------------------
     def _resolve(self, iq) -> Tuple[int, int, int]:
-        dev = _device_pointer(iq)
+        row = 2 * self.block_samples * self.blocks_per_launch       # the consecutive blocks of one stream
+        dev = _device_pointer(iq, self.n_streams, row)
         if dev is not None:
             return dev[0], 1, dev[1]
         arr = np.asarray(iq)
         if arr.dtype != np.uint8:
             raise TypeError("IQ blocks must be uint8 interleaved I,Q bytes")
+        if arr.ndim == 3 and arr.shape[1:] == (self.blocks_per_launch, 2 * self.block_samples) and arr[0].flags.c_contiguous:
+            arr = arr.reshape(arr.shape[0], -1) if arr.flags.c_contiguous else np.lib.stride_tricks.as_strided(
+                arr, (arr.shape[0], row), (arr.strides[0], 1))
         if arr.ndim == 1:
             arr = arr.reshape(1, -1)
-        if arr.shape != (self.n_streams, 2 * self.block_samples) or arr.strides[1] != 1:
-            raise ValueError(f"expected uint8 [{self.n_streams}, {2 * self.block_samples}], got {arr.shape}")
+        if arr.shape != (self.n_streams, row) or arr.strides[1] != 1:
+            raise ValueError(f"expected uint8 [{self.n_streams}, {row}], got {arr.shape}")
         self._keepalive = (self._keepalive + [arr])[-2:]
         return int(arr.ctypes.data), 0, int(arr.strides[0])
 
     def launch(self, iq) -> None:
-        """Enqueue one block for every stream (asynchronous)."""
+        """Enqueue one block (`blocks_per_launch` consecutive blocks) for every stream (asynchronous)."""
         ptr, on_dev, stride = self._resolve(iq)
         _check(self._lib.rt_engine_launch(self._h, ctypes.c_void_p(ptr), on_dev, stride))
 
     def fetch(self) -> np.ndarray:
-        """Wait for the last launch; candidate records sorted by (stream, fi, start)."""
+        """Wait for the oldest unfetched launch; candidate records sorted by (unit, fi, start).  If the launch produced more
+        records than `max_records`, the first ones are returned, `self.truncated` says how many are missing, and an error
+        is logged (the reference has no such limit: one noisy band must not take the other streams' detections down)."""
         n = ctypes.c_int32(0)
-        _check(self._lib.rt_engine_fetch(self._h, self._out.ctypes.data_as(ctypes.c_void_p), self.max_records, ctypes.byref(n)))
-        return self._out[: n.value].copy()
+        _check(self._lib.rt_engine_peek(self._h, ctypes.byref(n)))
+        out = np.empty(n.value, dtype=RECORD_DTYPE)
+        need = ctypes.c_int32(0)
+        rc = self._lib.rt_engine_fetch(self._h, out.ctypes.data_as(ctypes.c_void_p), n.value, ctypes.byref(need))
+        self.truncated = 0
+        if rc == RT_ERR_OVERFLOW:
+            self.truncated = need.value - n.value
+            logger.error("rt_engine: %d candidate records exceed max_records, %d dropped", need.value, self.truncated)
+        else:
+            _check(rc)
+        return out
 
     def process(self, iq) -> np.ndarray:
-        ptr, on_dev, stride = self._resolve(iq)
-        n = ctypes.c_int32(0)
-        _check(self._lib.rt_engine_process(self._h, ctypes.c_void_p(ptr), on_dev, stride,
-                                           self._out.ctypes.data_as(ctypes.c_void_p), self.max_records, ctypes.byref(n)))
-        return self._out[: n.value].copy()
+        self.launch(iq)
+        return self.fetch()
 
     def reset_stream(self, stream: int) -> None:
         _check(self._lib.rt_engine_reset_stream(self._h, stream))
@@ -225,6 +267,8 @@ class Engine:
     # -- parity hooks / timing ------------------------------------------------------------------
     def read_spectrogram(self, stream: int = 0) -> np.ndarray:
         """float32 [T, nperseg] of the last launch (= scipy's Sxx transposed)."""
+        if not 0 <= stream < self.n_units:
+            raise IndexError("no such analyzer unit")
         out = np.empty((self.T, self.nperseg), dtype=np.float32)
         _check(self._lib.rt_engine_read_spectrogram(self._h, stream, out.ctypes.data_as(ctypes.c_void_p)))
         return out
@@ -234,8 +278,9 @@ class Engine:
         _check(self._lib.rt_engine_read_row_means(self._h, stream, out.ctypes.data_as(ctypes.c_void_p)))
         return out
 
-    def enable_timing(self, on: bool = True) -> None:
-        _check(self._lib.rt_engine_enable_timing(self._h, int(on)))
+    def enable_timing(self, period: int = 4) -> None:
+        """Bracket the kernels of every `period`-th launch with CUDA events (0 / False: off)."""
+        _check(self._lib.rt_engine_enable_timing(self._h, int(period)))
 
     def timing(self, reset: bool = False) -> dict:
         t = RtTiming()

@@ -242,3 +242,58 @@ def test_cheap_predicate_equals_exact_predicate_on_cpu(tmp_path):
     subprocess.run(["g++", "-O2", "-o", str(exe), os.path.join(ROOT, "tests", "pred_host_check.cpp")], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert int(out[0]) > 10_000_000 and int(out[1]) == 0
+
+
+def test_shadow_sweep_equals_the_pairwise_definition_with_ties():
+    """The O(S log S) shadow filter against the pairwise definition (analyze.py:283-313) on random lists with equal start times,
+    zero durations, touching intervals and equal loudness; and a whole batch evaluated in one pass == unit by unit."""
+    from pyradiotracking_b200.analyze import _UNIT_GAP_US
+
+    def pairwise(ts, du, mx):
+        te = ts + du
+        return np.array([bool((((ts[i] <= te) & (te[i] >= ts)) & (mx > mx[i])).any()) for i in range(len(ts))], dtype=bool)
+
+    rng = np.random.default_rng(11)
+    for _ in range(300):
+        n = int(rng.integers(0, 70))
+        ts = rng.integers(0, 120, n) * 1000
+        du = rng.integers(0, 40, n) * 1000
+        mx = np.round(rng.normal(-70, 3, n), 0)
+        assert np.array_equal(shadow_mask(ts, du, mx), pairwise(ts, du, mx))
+    unit = np.sort(rng.integers(0, 5, 400))
+    ts = rng.integers(0, 900_000, 400)
+    du = rng.integers(8000, 40000, 400)
+    mx = rng.normal(-70, 4, 400)
+    whole = shadow_mask(ts + unit * _UNIT_GAP_US, du, mx)
+    for u in range(5):
+        m = unit == u
+        assert np.array_equal(whole[m], pairwise(ts[m], du[m], mx[m]))
+
+
+def test_unit_timestamps_and_parity_counters():
+    """blocks_per_launch: unit u = stream * B + block starts `block` callback lengths after the launch (the reference's `_ts +=
+    buffer_len_dt`, analyze.py:221); and oracle/check.py (the bench's parity gate) counts an identical result as identical."""
+    from oracle import check as C
+
+    w = synth.C1
+    ba = BatchAnalyzer(devices=["a", "b"], calibration_db=[0.0, 1.0], sample_rate=w.sample_rate, center_freq=w.center_freq,
+                       fft_nperseg=256, fft_window="hamming", signal_min_duration_ms=8, signal_max_duration_ms=40,
+                       signal_threshold_dbw=-90.0, snr_threshold_db=5.0, blocks_per_launch=3)
+    t0 = datetime.datetime(2026, 1, 1)
+    uts = ba.unit_ts([t0, t0 + datetime.timedelta(seconds=5)])
+    ts, step = t0, datetime.timedelta(seconds=w.block_samples / w.sample_rate)
+    for b in range(3):
+        assert uts[b] == ts and uts[3 + b] == ts + datetime.timedelta(seconds=5)
+        ts += step
+    with pytest.raises(ValueError, match="powers of two"):
+        BatchAnalyzer(devices=["a"], calibration_db=[0.0], sample_rate=300000, center_freq=0, fft_nperseg=250, fft_window="hamming",
+                      signal_min_duration_ms=8, signal_max_duration_ms=40, signal_threshold_dbw=-90.0, snr_threshold_db=5.0)
+    P = R.Params.make(sample_rate=w.sample_rate)
+    ora = R.OracleAnalyzer(P)
+    cap = synth.make_stream(w, 0, 1)
+    _, _, S, found, kept = ora.process_block(cap[0], t0)
+    tot = C.new_totals()
+    C.add_block(tot, P, S, None, found, kept, list(found), [d.key() for d in found], list(kept), S.T.astype(np.float32), S.mean(axis=1).astype(np.float32))
+    assert C.verdict(tot) and tot["key_mismatches"] == 0 and tot["cells_checked"] > 0
+    C.add_block(tot, P, S, None, found, kept, list(found)[1:], [d.key() for d in found][1:], list(kept))
+    assert tot["key_mismatches"] == 1 and not C.verdict(tot)

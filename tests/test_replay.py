@@ -79,3 +79,22 @@ def test_replay_of_files_equals_feeding_the_blocks_directly(tmp_path):
     finally:
         a.close()
         b.close()
+
+
+def test_reader_groups_of_blocks_and_pads_the_last_group(tmp_path):
+    """blocks_per_read = B (rt_config.blocks_per_launch): items are B consecutive blocks per stream; 7 blocks = 2 groups of 3 + 1
+    block padded with zero bytes."""
+    rng = np.random.default_rng(2)
+    N = 500
+    a = rng.integers(1, 256, 2 * N * 7 + 5, dtype=np.uint8)
+    b = rng.integers(1, 256, 2 * N * 7, dtype=np.uint8)
+    paths = _write(tmp_path, [a, b])
+    r = CaptureReader(paths, N, pinned=False, blocks_per_read=3)
+    assert r.n_blocks == 7
+    got = [(k, blk.copy()) for k, blk in r]
+    assert [k for k, _ in got] == [0, 3, 6]
+    for k, blk in got:
+        assert blk.shape == (2, 3 * 2 * N)
+        have = min(3, 7 - k) * 2 * N
+        assert np.array_equal(blk[0][:have], a[2 * N * k: 2 * N * k + have]) and np.array_equal(blk[1][:have], b[2 * N * k: 2 * N * k + have])
+        assert not blk[:, have:].any()

@@ -17,7 +17,7 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 
-def run(name, w, n_streams, steps, warmup, torch, synth, BatchAnalyzer, fft_impl=0, tile=None):
+def run(name, w, n_streams, steps, warmup, torch, synth, BatchAnalyzer, fft_impl=0, kernel_timing=4, **engine_kw):
     distinct = [synth.make_stream(w, i, 2) for i in range(min(4, n_streams))]
     host = np.empty((2, n_streams, w.block_bytes), dtype=np.uint8)
     for s in range(n_streams):
@@ -27,15 +27,15 @@ def run(name, w, n_streams, steps, warmup, torch, synth, BatchAnalyzer, fft_impl
                        sample_rate=w.sample_rate, center_freq=w.center_freq, fft_nperseg=w.nperseg, fft_window="hamming",
                        signal_min_duration_ms=w.signal_min_duration_ms, signal_max_duration_ms=w.signal_max_duration_ms,
                        signal_threshold_dbw=w.signal_threshold_dbw, snr_threshold_db=w.snr_threshold_db,
-                       sdr_callback_length=w.block_samples, cuda_device=0, fft_impl=fft_impl, max_records=1 << 18)
+                       sdr_callback_length=w.block_samples, cuda_device=0, fft_impl=fft_impl, **engine_kw)
     eng = ba.engine
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
     for i in range(warmup):
         eng.launch(dev[i % 2])
     n_rec = len(eng.fetch())
-    timing = os.environ.get("RT_BENCH_NO_KERNEL_TIMING") is None      # per-kernel events cost a few us of launch gaps per step
-    eng.enable_timing(timing)
+    timing = kernel_timing > 0      # per-kernel events cost a few us of launch gaps per step: every `kernel_timing`-th launch only
+    eng.enable_timing(kernel_timing)
     eng.timing(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -46,7 +46,7 @@ def run(name, w, n_streams, steps, warmup, torch, synth, BatchAnalyzer, fft_impl
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     tim = eng.timing(reset=True)
-    eng.enable_timing(False)
+    eng.enable_timing(0)
     if not timing:
         tim = {"spectrogram_ms": 0.0, "probe_ms": 0.0, "extract_ms": 0.0, "launches": 1}
     n_rec = len(eng.fetch())
@@ -57,7 +57,7 @@ def run(name, w, n_streams, steps, warmup, torch, synth, BatchAnalyzer, fft_impl
            "algorithmic_gb_per_s": round(2 * samples / (ms * 1e-3) / 1e9, 1),
            "spectrogram_ms": round(tim["spectrogram_ms"] / tim["launches"], 4),
            "probe_ms": round(tim["probe_ms"] / tim["launches"], 4), "extract_ms": round(tim["extract_ms"] / tim["launches"], 4),
-           "records_per_step": n_rec, "work_items": work, "fft_impl": fft_impl}
+           "records_per_step": n_rec, "work_items": work, "fft_impl": fft_impl, "engine": engine_kw}
     ba.close()
     del dev
     torch.cuda.empty_cache()

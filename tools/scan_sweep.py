@@ -1,5 +1,8 @@
 #!/usr/bin/env python
-"""configs[1] step time under the engine's schedule / scan knobs (environment variables read by rt_engine_create).
+"""configs[1] step time under the engine's schedule knobs (rt_config.scan_schedule / launch_streams / chunk_segs).
+
+The kernel variants that round 1 swept through environment variables live in tools/ now (spectro256_lab.cuh); what is left
+to sweep in the product is what rt_config exposes.
 
 Run on the GPU box:  python tools/scan_sweep.py [--steps 20]   (one JSON line per variant)
 """
@@ -12,22 +15,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+SERIAL, OVERLAP, LEAN = 1, 2, 3
 VARIANTS = [
-    ("default: v7n, lean scan 8 CTAs/SM <1,0>, two launch streams", {}),
-    ("one launch stream", {"RT_LAUNCH_STREAMS": "1"}),
-    ("lean extraction windows <2,2>", {"RT_LEAN_EX": "22"}),
-    ("lean scan 1 CTA/SM", {"RT_SCAN_LEAN": "1"}),
-    ("full-size scan kernels", {"RT_SCAN_LEAN": "0"}),
-    ("unpinned v7", {"RT_V7_MAXR": "0"}),
-    ("v7 112 registers", {"RT_V7_MAXR": "112"}),
-    ("v7n + ALU byte sums + packed row sums", {"RT_V7_MAXR": "-4"}),
-    ("probe plane", {"RT_PROBE_PLANE": "1"}),
-    ("S time-blocked 8", {"RT_S_LAYOUT": "8"}),
-    ("S time-blocked 32", {"RT_S_LAYOUT": "32"}),
-    ("chunk 256", {"RT_CHUNK_SEGS": "256"}),
-    ("scan reads an L2-resident S (timing experiment, wrong results)", {"RT_SCAN_EXPERIMENT_L2": "1"}),
-    ("per-kernel events on every launch", {"RT_TIMING_PERIOD": "1"}),
-    ("serial", {"RT_SCAN_OVERLAP": "0"}),
+    ("default: lean scan, two launch streams, chunks of 192 segments", {}),
+    ("one launch stream", {"launch_streams": 1}),
+    ("full-size scan kernels on the scan stream", {"scan_schedule": OVERLAP}),
+    ("serial (everything on the launch stream)", {"scan_schedule": SERIAL}),
+    ("chunks of 128 segments", {"chunk_segs": 128}),
+    ("chunks of 256 segments", {"chunk_segs": 256}),
+    ("per-kernel events on every launch", {"kernel_timing": 1}),
+    ("no per-kernel events", {"kernel_timing": 0}),
 ]
 
 
@@ -35,7 +32,6 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=4)
-    ap.add_argument("--extra", action="append", default=[], help="NAME=VALUE applied to every variant")
     args = ap.parse_args()
     import contextlib
     import io
@@ -46,20 +42,11 @@ def main():
     from pyradiotracking_b200.analyze import BatchAnalyzer
     from tools.bench_configs import run
 
-    keys = {"RT_PROBE_PLANE", "RT_SCAN_OVERLAP", "RT_SCAN_LEAN", "RT_V7_MAXR", "RT_LEAN_NO_CARVEOUT", "RT_CHUNK_SEGS", "RT_SCAN_EXPERIMENT_L2", "RT_S_LAYOUT", "RT_LEAN_EX", "RT_BENCH_NO_KERNEL_TIMING", "RT_TIMING_PERIOD", "RT_LAUNCH_STREAMS"} | {kv.split("=")[0] for kv in args.extra}
-    for name, env in VARIANTS:
-        for k in keys:
-            os.environ.pop(k, None)
-        for kv in args.extra:
-            k, v = kv.split("=", 1)
-            os.environ[k] = v
-        os.environ.update(env)
+    for name, kw in VARIANTS:
         buf = io.StringIO()
         with contextlib.redirect_stdout(buf):
-            run(name, synth.C2, 64, args.steps, args.warmup, torch, synth, BatchAnalyzer)
-        row = json.loads(buf.getvalue().strip().splitlines()[-1])
-        row["env"] = env
-        print(json.dumps(row), flush=True)
+            run(name, synth.C2, 64, args.steps, args.warmup, torch, synth, BatchAnalyzer, **kw)
+        print(buf.getvalue().strip().splitlines()[-1], flush=True)
 
 
 if __name__ == "__main__":

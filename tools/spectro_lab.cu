@@ -9,7 +9,7 @@
 #include <string>
 #include <cstring>
 
-#include "../pyradiotracking_b200/csrc/spectro256.cuh"
+#include "spectro256_lab.cuh"
 
 using namespace rt;
 

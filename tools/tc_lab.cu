@@ -9,7 +9,7 @@
 #include <cstring>
 #include <algorithm>
 
-#include "../pyradiotracking_b200/csrc/spectro_tc256.cuh"
+#include "spectro_tc256_lab.cuh"
 
 using namespace rt;
 
@@ -56,12 +56,12 @@ int main(int argc, char** argv) {
     SpectroArgs a7;
     a7.iq = d_iq; a7.stream_stride = stride; a7.n = 256; a7.T = T; a7.chunk_segs = chunk; a7.n_chunks = n_chunks;
     a7.win = d_win; a7.tw = d_tw; a7.S = d_S7; a7.S_stream_stride = (size_t)T * 256; a7.part = d_part7;
-    CK(cudaFuncSetAttribute(spectro_reg256_v7<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, R256v7::SMEM));
+    CK(cudaFuncSetAttribute(spectro_reg256_v7n<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, R256v7::SMEM));
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     float best7 = 1e9f;
     for (int i = 0; i < 3 + reps; ++i) {
         CK(cudaEventRecord(e0));
-        spectro_reg256_v7<true><<<dim3(n_chunks, streams), R256v7::THREADS, R256v7::SMEM>>>(a7);
+        spectro_reg256_v7n<true><<<dim3(n_chunks, streams), R256v7::THREADS, R256v7::SMEM>>>(a7);
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (i >= 3) best7 = std::min(best7, ms);
     }
