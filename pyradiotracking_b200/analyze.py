@@ -27,6 +27,14 @@ import numpy as np
 from . import engine as _engine
 from .messages import from_dB, message_types
 
+try:
+    from . import _rtfinal                  # csrc/rt_pyfinal.c: the Signal-object builder of the finaliser
+except ImportError:                         # never built in this tree: build it now (gcc), like engine.load_library does with nvcc
+    from . import build as _build
+
+    _build.build_pyfinal()
+    from . import _rtfinal
+
 logger = logging.getLogger(__name__)
 UTC = datetime.timezone.utc
 
@@ -123,12 +131,17 @@ def shadow_mask(ts_us: np.ndarray, dur_us: np.ndarray, max_dbw: np.ndarray) -> n
     ts = np.asarray(ts_us, dtype=np.int64)
     te = ts + np.asarray(dur_us, dtype=np.int64)
     mx = np.asarray(max_dbw, dtype=np.float64)
-    U, lo = np.unique(ts, return_inverse=True)            # lo[i]: index of ts[i] among the sorted distinct start times
+    order = np.argsort(ts, kind="stable")
+    ts_s = ts[order]
+    first = np.r_[True, ts_s[1:] != ts_s[:-1]]             # first signal of every distinct start time
+    U = ts_s[first]
+    lo = np.empty(n, dtype=np.int64)
+    lo[order] = np.cumsum(first) - 1                       # lo[i]: index of ts[i] among the sorted distinct start times
     hi = np.searchsorted(U, te, side="right") - 1         # last distinct start time <= te[i] (>= lo[i]: durations are >= 0)
     m = len(U)
-    K = max(1, int(m).bit_length())
+    K = int(np.max(hi - lo + 1)).bit_length()             # levels needed: 2^(K-1) <= longest range of start times
     st = np.full((K, m), -np.inf)                         # st[k][u] = max over start times u .. u + 2^k - 1
-    np.maximum.at(st[0], lo, mx)
+    st[0] = np.maximum.reduceat(mx[order], np.flatnonzero(first))
     for k in range(1, K):
         h = 1 << (k - 1)
         st[k] = st[k - 1]
@@ -136,9 +149,14 @@ def shadow_mask(ts_us: np.ndarray, dur_us: np.ndarray, max_dbw: np.ndarray) -> n
     k = np.frexp((hi - lo + 1).astype(np.float64))[1] - 1     # floor(log2(range length))
     off = hi - (1 << k) + 1
     starts_inside = np.maximum(st[k, lo], st[k, off])
-    rt = np.full((K, m), -np.inf)                         # pending chmax updates of the blocks [u, u + 2^k)
-    np.maximum.at(rt, (k, lo), mx)
-    np.maximum.at(rt, (k, off), mx)
+    rt = np.full(K * m, -np.inf)                          # pending chmax updates of the blocks [u, u + 2^k), flattened [k][u]
+    cell = np.concatenate((k * m + lo, k * m + off))      # two (overlapping) blocks per interval; grouped maximum per cell
+    val = np.concatenate((mx, mx))
+    o2 = np.argsort(cell, kind="stable")
+    cell_s = cell[o2]
+    g = np.flatnonzero(np.r_[True, cell_s[1:] != cell_s[:-1]])
+    rt[cell_s[g]] = np.maximum.reduceat(val[o2], g)
+    rt = rt.reshape(K, m)
     for kk in range(K - 1, 0, -1):
         h = 1 << (kk - 1)
         np.maximum(rt[kk - 1], rt[kk], out=rt[kk - 1])
@@ -193,6 +211,9 @@ class BatchAnalyzer:
         self._engine: Optional[_engine.Engine] = None
         self.last_record_count = 0          # candidate records copied back by the last collect()
         self.Signal, self.StateMessage = message_types()
+        # the two known Signal classes only store their arguments (radiotracking/__init__.py:136-170): their instances may be
+        # filled directly; any other class is called like the reference calls it
+        self._direct = self.Signal.__module__ in ("radiotracking", "pyradiotracking_b200.messages")
 
     # the engine is created on first use: after a fork, inside the analyzer process
     @property
@@ -261,16 +282,23 @@ class BatchAnalyzer:
 
     def build_signals(self, fin: "Finalized", ts_start: Sequence[datetime.datetime], keep: Optional[np.ndarray] = None):
         """Signal objects per analyzer unit, in the reference's emission order (bin, then time), for the rows of
-        `fin` selected by `keep` (default: all).  `ts_start`: one per stream (the first block of the launch)."""
-        out = [[] for _ in range(self.n_units)]
-        Signal, devices, bpl = self.Signal, self.devices, self.blocks_per_launch
+        `fin` selected by `keep` (default: all).  `ts_start`: one per stream (the first block of the launch).
+
+        The objects are built by the C helper `_rtfinal` (csrc/rt_pyfinal.c): `ts = (ts_start + timedelta(start_dt)).astimezone(utc)`
+        (analyze.py:434,449) is evaluated as `ts_start.astimezone(utc) + timedelta` per unit, which is the same instant unless
+        the local UTC offset changes inside the block -- checked per unit, the plain Python expression is used then."""
         uts = self.unit_ts(ts_start)
-        idx = np.arange(len(fin.stream)) if keep is None else np.nonzero(keep)[0]
-        td = datetime.timedelta
-        for u, off, dur, f, mx, av, sd, no, sn in zip(
-                fin.stream[idx].tolist(), fin.ts_off_us[idx].tolist(), fin.dur_us[idx].tolist(),
-                fin.frequency[idx].tolist(), fin.max[idx].tolist(), fin.avg[idx].tolist(), fin.std[idx].tolist(),
-                fin.noise[idx].tolist(), fin.snr[idx].tolist()):
+        idx = slice(None) if keep is None else np.nonzero(keep)[0]
+        cols = [np.ascontiguousarray(c[idx], dtype=np.int64) for c in (fin.stream, fin.ts_off_us, fin.dur_us)]
+        cols += [np.ascontiguousarray(c[idx], dtype=np.float64) for c in (fin.frequency, fin.max, fin.avg, fin.std, fin.noise, fin.snr)]
+        block = datetime.timedelta(seconds=self.block_samples / self.sample_rate)
+        base = [t.astimezone(UTC) for t in uts]
+        if all((t + block).astimezone(UTC) - b == block and b - (t - block).astimezone(UTC) == block for t, b in zip(uts, base)):
+            devices = self.devices if self.blocks_per_launch == 1 else [d for d in self.devices for _ in range(self.blocks_per_launch)]
+            return _rtfinal.build_signals(self.Signal, self._direct, devices, base, *cols)
+        out = [[] for _ in range(self.n_units)]                 # a UTC-offset change inside a block: the reference's expression
+        Signal, devices, bpl, td = self.Signal, self.devices, self.blocks_per_launch, datetime.timedelta
+        for u, off, dur, f, mx, av, sd, no, sn in zip(*[c.tolist() for c in cols]):
             ts = (uts[u] + td(microseconds=off)).astimezone(UTC)
             out[u].append(Signal(devices[u // bpl], ts, f, td(microseconds=dur), mx, av, sd, no, sn))
         return out

@@ -52,12 +52,35 @@ def run(name, w, n_streams, steps, warmup, torch, synth, BatchAnalyzer, fft_impl
     n_rec = len(eng.fetch())
     work, _ = eng.last_counts()
     samples = n_streams * w.block_samples
+    # end to end through BatchAnalyzer.submit / collect on pinned host buffers (two launches in flight), like bench.py's e2e
+    import datetime
+    import time
+    pin = torch.empty(host.shape, dtype=torch.uint8, pin_memory=True)
+    pin.numpy()[...] = host
+    hp = pin.numpy()
+    ts = [datetime.datetime(2026, 1, 1)] * n_streams
+    for i in range(2):
+        ba.process_blocks(hp[i % 2], ts)
+    for k in ba.timings:
+        ba.timings[k] = 0
+    n_e2e = max(4, min(steps, 12))
+    kept = 0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ba.submit(hp[0])
+    for i in range(n_e2e):
+        if i + 1 < n_e2e:
+            ba.submit(hp[(i + 1) % 2])
+        kept += sum(len(r[0]) for r in ba.collect(ts))
+    e2e_s = (time.perf_counter() - t0) / n_e2e
     out = {"config": name, "streams": n_streams, "nperseg": w.nperseg, "block_samples": w.block_samples,
            "ms_per_step": round(ms, 4), "msamples_per_s": round(samples / (ms * 1e-3) / 1e6),
            "algorithmic_gb_per_s": round(2 * samples / (ms * 1e-3) / 1e9, 1),
            "spectrogram_ms": round(tim["spectrogram_ms"] / tim["launches"], 4),
            "probe_ms": round(tim["probe_ms"] / tim["launches"], 4), "extract_ms": round(tim["extract_ms"] / tim["launches"], 4),
-           "records_per_step": n_rec, "work_items": work, "fft_impl": fft_impl, "engine": engine_kw}
+           "records_per_step": n_rec, "work_items": work, "fft_impl": fft_impl, "engine": engine_kw,
+           "e2e_msamples_per_s": round(samples / e2e_s / 1e6), "e2e_ms_per_step": round(1e3 * e2e_s, 3), "e2e_signals_kept_per_step": round(kept / n_e2e, 1),
+           "e2e_host_ms_per_step": {k: round(1e3 * v / n_e2e, 3) for k, v in ba.timings.items() if k.endswith("_s")}}
     ba.close()
     del dev
     torch.cuda.empty_cache()
