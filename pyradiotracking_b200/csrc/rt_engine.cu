@@ -671,6 +671,7 @@ struct rt_engine {
     int lean_ctas = 148;
     float* d_win = nullptr;
     float2* d_tw = nullptr;
+    float2* d_tw1 = nullptr;                 // spectro_r16: pass-1 twiddle table [15][n / 16]
     // three spectrogram buffers: launch i writes S[i % 3] while the scan of launch i-1 still reads
     // S[(i-1) % 3] (its block) and S[(i-2) % 3] (its carry) on the scan stream
     float* d_S[RT_SBUFS] = {nullptr, nullptr, nullptr};
@@ -753,7 +754,7 @@ void free_engine(rt_engine* e) {
     if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     for (auto& s : e->ev_pool)
         for (auto& ev : s.ev) cudaEventDestroy(ev);
-    cudaFree(e->d_win); cudaFree(e->d_tw);
+    cudaFree(e->d_win); cudaFree(e->d_tw); cudaFree(e->d_tw1);
     for (auto& p : e->d_S) cudaFree(p);
     for (int k = 0; k < RT_SLOTS; ++k) { cudaFree(e->d_part[k]); cudaFree(e->d_avg[k]); cudaFree(e->d_ctr[k]); cudaFree(e->d_rec[k]); }
     cudaFree(e->d_bmat); cudaFree(e->d_thr); cudaFree(e->d_hasprev);
@@ -862,10 +863,11 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     }
     e->n_chunks = (e->T + e->chunk_segs - 1) / e->chunk_segs;
     if (e->r16) {
-        // segments are dealt round-robin over n_chunks CTAs (x teams) per unit; 296 = 148 SMs x 2 resident CTAs
+        // segments are dealt round-robin over n_chunks CTAs (x teams) per unit: 148 SMs x the resident CTAs (3 at 1024, 2 at 4096)
         const int teams = n == 4096 ? 1 : 4;
+        const int resident = 148 * (n == 4096 ? rt::R16Cfg<4096>::CTAS_PER_SM : rt::R16Cfg<1024>::CTAS_PER_SM);
         // (depends on T only, like chunk_segs above: the same row means alone and inside a batch)
-        e->n_chunks = std::min(296, (e->T + teams - 1) / teams);
+        e->n_chunks = std::min(resident, (e->T + teams - 1) / teams);
         e->chunk_segs = (e->T + e->n_chunks - 1) / e->n_chunks;      // informational
     }
     e->s_stride = e->tc256 ? (size_t)((e->T + 31) / 32) * 8192 : (size_t)e->T * n;
@@ -981,6 +983,12 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     e->h_hasprev_units.assign(e->n_units, 0);
     e->hasprev_dirty = true;
     if (e->r16) {
+        const int bt = n / 16;
+        std::vector<float2> htw1((size_t)15 * bt);
+        for (int i = 1; i < 16; ++i)
+            for (int b = 0; b < bt; ++b) htw1[(size_t)(i - 1) * bt + b] = htw[(b * i) & (n - 1)];
+        CUE(cudaMalloc(&e->d_tw1, htw1.size() * sizeof(float2)));
+        CUE(cudaMemcpy(e->d_tw1, htw1.data(), htw1.size() * sizeof(float2), cudaMemcpyHostToDevice));
         if (n == 4096) CUE(cudaFuncSetAttribute(rt::spectro_r16_k<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R16Cfg<4096>::SMEM));
         else CUE(cudaFuncSetAttribute(rt::spectro_r16_k<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R16Cfg<1024>::SMEM));
     }
@@ -1095,7 +1103,7 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     sa.iq = d_iq; sa.stream_stride = stride; sa.n = e->n; sa.T = e->T;
     sa.bpl = e->bpl; sa.block_bytes = e->block_bytes;
     sa.chunk_segs = e->chunk_segs; sa.n_chunks = e->n_chunks;
-    sa.win = e->d_win; sa.tw = e->d_tw; sa.S = e->d_S[next]; sa.part = e->d_part[slot];
+    sa.win = e->d_win; sa.tw = e->d_tw; sa.tw1 = e->d_tw1; sa.S = e->d_S[next]; sa.part = e->d_part[slot];
     sa.S_stream_stride = e->s_stride;
     const bool use_reg = e->reg256;
     dim3 grid(e->n_chunks, e->n_units);

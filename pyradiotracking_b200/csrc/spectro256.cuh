@@ -22,6 +22,7 @@ struct SpectroArgs {
     int n, T, chunk_segs, n_chunks;
     const float* win;      // window * sqrt(1/(fs*sum(w^2))) / 127.5
     const float2* tw;      // exp(-2 pi i k / n)
+    const float2* tw1 = nullptr;   // spectro_r16: pass-1 twiddles exp(-2 pi i (b i) / n) as [i - 1][b], i = 1..15, b < n / 16
     float* S;              // generic kernel: [stream][T][n]; register kernel: [stream][T][pos(bin)] (see rt_engine.cu)
     size_t S_stream_stride;  // floats per stream
     float* part;           // [stream][chunk][n]   (FFT bin order; spectro_reg256_v7: PERM position order, like its S rows)

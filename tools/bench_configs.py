@@ -91,6 +91,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--only", default="", help="run only the configurations whose name contains this")
     args = ap.parse_args()
     import torch
 
@@ -99,6 +100,13 @@ def main():
     from pyradiotracking_b200.analyze import BatchAnalyzer
 
     a = (args.steps, args.warmup, torch, synth, BatchAnalyzer)
+    global run
+    _run = run
+
+    def run(name, *rest, **kw):
+        if args.only in name:
+            _run(name, *rest, **kw)
+
     run("configs[0] single 300 kS/s stream", synth.C1, 1, *a)
     run("one 2.4 MS/s stream (a single live SDR at the RTL-SDR maximum)", synth.C2, 1, *a)
     run("configs[1] 64 x 2.4 MS/s (register kernel)", synth.C2, 64, *a)
