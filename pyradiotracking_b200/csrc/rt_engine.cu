@@ -254,7 +254,9 @@ struct ScanArgs {
     float snr;
     int n, T, stride, n_probes, min_cols, max_cols;
     int n_streams_scan;    // streams of the batch (lean probe kernel: tiles are walked with a grid stride)
-    uint2* work;           // (stream << 16 | fi, ti | (chain members - 1) << 24): consecutive probe columns ti, ti + stride, ...
+    uint4* work;           // (stream << 16 | fi, ti | (chain members - 1) << 24, row mean, threshold): consecutive probe columns ti, ti + stride, ...;
+                           // the two floats save the extraction warp two dependent round trips in front of its first cells
+    int max_work;          // capacity of the work list (worst case: every probe column of every bin)
     int* counters;         // [0] work items, [1] records
     rt_record* rec;
     int max_records;
@@ -262,9 +264,6 @@ struct ScanArgs {
 
 constexpr int PROBE_QUICK = 3;   // cells examined on each side before handing a probe hit to a warp
 constexpr int PROBE_CHAIN = 8;   // consecutive surviving probe hits of a bin handed to ONE extraction warp (bounds its serial work)
-// extraction kernel: EX_W 32-cell windows per memory round trip, EX_F forward windows fetched together with the backward
-// window in a work item's first round trip (template parameters: 4 / 4 stand-alone, 2 / 2 for the 32-register lean variant)
-
 constexpr int PROBE_PPT = 32;    // probe columns per thread: their loads are in flight together, and the row-mean prologue
                                  // is repeated once per PROBE_PPT columns (8 -> 32: 5x fewer instructions, 29 -> see DESIGN 5.4)
 
@@ -373,7 +372,7 @@ __global__ void probe_kernel(ScanArgs a) {
         while (head + len < 32 && ((head + len) % PROBE_CHAIN) != 0 && ((live >> (head + len)) & 1u)) ++len;
         live &= ~(((1u << len) - 1u) << head);
         const int slot = atomicAdd(&a.counters[0], 1);
-        a.work[slot] = make_uint2(((unsigned)s << 16) | (unsigned)fi, (unsigned)((g * PPT + head) * a.stride) | ((unsigned)(len - 1) << 24));
+        a.work[slot] = make_uint4(((unsigned)s << 16) | (unsigned)fi, (unsigned)((g * PPT + head) * a.stride) | ((unsigned)(len - 1) << 24), __float_as_uint(avg), __float_as_uint(thr));
     }
 }
 
@@ -412,7 +411,7 @@ __global__ void __launch_bounds__(128, 16) probe_lean_kernel(ScanArgs a) {
         auto flush = [&]() {
             if (len > 0) {
                 const int slot = atomicAdd(&a.counters[0], 1);
-                a.work[slot] = make_uint2(((unsigned)s << 16) | (unsigned)fi, (unsigned)((g * LEAN_PPT + head) * a.stride) | ((unsigned)(len - 1) << 24));
+                a.work[slot] = make_uint4(((unsigned)s << 16) | (unsigned)fi, (unsigned)((g * LEAN_PPT + head) * a.stride) | ((unsigned)(len - 1) << 24), __float_as_uint(avg), __float_as_uint(thr));
             }
             len = 0;
         };
@@ -456,69 +455,87 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// MINB > 0: 128-thread CTAs with at least MINB of them resident per SM (register cap), so that one wave of warps covers the
-// work list: every item is one chain of dependent memory round trips, a second wave doubles the kernel time
-template <int TILE, int MINB, int EX_W = 4, int EX_F = 4>
-__global__ void __launch_bounds__(MINB > 0 ? 128 : 1024, MINB > 0 ? MINB : 1) extract_kernel(ScanArgs a) {
+// extract2_kernel: one warp per work item (the round-1 extract_kernel at about half its memory sectors and round trips).  Measured
+// (tools/scan_skip.py, configs[1]): beside the spectrogram of the next launch the extraction alone costs the step 23 of its 30 us
+// of scan overhead, and that cost follows the number of scattered 32-byte sectors it reads (a first version with wide
+// speculative fetches -- 4 round trips per run instead of 11, the same ~340 sectors -- was 4 us SLOWER).
+//   * cells travel in ALIGNED blocks of 32 columns (lane = column & 31), the probe's own block first, then one block down
+//     and one block up per round trip for as long as that side of the run is still open: nothing is fetched speculatively;
+//   * max / sum / sum dB / sum dB^2 are accumulated while the blocks pass through the registers -- no second pass over the
+//     run, which was 150 of the ~340 sectors of a typical 150-column pulse;
+//   * one fixed per-lane order of the float64 sums, so every schedule returns the same bits.
+template <int TILE, int MINB>
+__global__ void __launch_bounds__(128, MINB) extract2_kernel(ScanArgs a) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    // the first work item is fetched together with the item count (the list is allocated for the worst case, a stale entry is
+    // harmless): one round trip in front of the first cells instead of three (count -> item -> row mean / threshold)
+    uint4 wk = a.work[min(warp, a.max_work - 1)];
     const int n_work = a.counters[0];
     const int T = a.T, n = a.n;
 
     for (int item = warp; item < n_work; item += n_warps) {
-        const uint2 wk = a.work[item];
+        if (item != warp) wk = a.work[item];
         const int s = wk.x >> 16, fi = wk.x & 0xffff, ti0 = (int)(wk.y & 0xffffffu), members = (int)(wk.y >> 24) + 1;
         const CellRef col = CellRef::make<TILE>(a.S, a.stream_stride, s, fi, n);
-        // carry (analyze.py:383-398): the previous block of this stream is the previous unit of the same launch, or -- for
-        // the first block of a launch -- the last unit of the stream in the previous launch's buffer
-        const bool first_blk = a.bpl == 1 || (s % a.bpl) == 0;
-        const CellRef pcol = first_blk ? CellRef::make<TILE>(a.Sprev, a.stream_stride, s + a.bpl - 1, fi, n)
-                                       : CellRef::make<TILE>(a.S, a.stream_stride, s - 1, fi, n);
-        const float thr = a.thr[s], avg = a.avg[s * n + fi], snr = a.snr;
+        const float thr = __uint_as_float(wk.w), avg = __uint_as_float(wk.z), snr = a.snr;
         const Pred pred(thr, avg, snr);
+        const int span_cap = a.max_cols + 2;             // a run longer than this fails the duration test anyway
         int skip_to = 0;                                 // every cell in [previous member's probe, skip_to) is known to be above
       for (int mem = 0; mem < members; ++mem) {
         const int ti = ti0 + mem * a.stride;
         if (ti < skip_to) continue;                      // inside the run the previous member evaluated (ti_skip, analyze.py:366)
+        const int lo_lim = max(ti - a.stride, 0);        // the backward scan stops at the previous probe column (analyze.py:366)
+        const int bh = ti >> 5, tl = ti & 31;
 
-        // ---- round 1: the backward window [ti - stride, ti) and the first forward windows are independent loads: one memory
-        // round trip for both (after the probe kernel's chaining most work items own their run, so the forward cells are
-        // rarely wasted).  Backward: nearest not-above cell; if there is none and the previous probe column exists, that
-        // probe already owns this run (ti_skip, analyze.py:366).
-        const int lo_lim = max(ti - a.stride, 0);
-        float pb[EX_W], pf[EX_F > 0 ? EX_F : 1];          // EX_F == 0: no speculative forward fetch (fewer sectors, one more round trip)
-#pragma unroll
-        for (int w = 0; w < EX_W; ++w) {
-            const int t = ti - 1 - 32 * w - lane;
-            pb[w] = (t >= lo_lim) ? col.at<TILE>(t) : -1.f;          // -1: outside the window
+        // statistics over data = [start, end) (analyze.py:436-447), accumulated as the cells arrive
+        float mx = 0.f;
+        double sum = 0.0, sdb = 0.0, sdb2 = 0.0;
+        auto acc = [&](float p) {
+            mx = fmaxf(mx, p);
+            sum += (double)p;
+            // dB of one cell in float (MUFU.LG2: ~1e-6 dB absolute error, the record tolerance is 5e-4 dB); the sums stay float64
+            const double db = (double)(3.0102999566398120f * __log2f(p));
+            sdb += db;
+            sdb2 += db * db;
+        };
+
+        int nb = -1, end = -1;                           // nearest not-above cell below / above the probe column
+        {                                                // the probe's own block serves both directions
+            const int t = 32 * bh + lane;
+            const bool valid = t >= lo_lim && t < T;
+            const float p = valid ? col.at<TILE>(t) : 0.f;
+            const unsigned m = __ballot_sync(0xffffffffu, valid && !pred(p));
+            const unsigned mb = m & ((1u << tl) - 1u), mf = m & ~((2u << tl) - 1u);      // tl == 31: no lane above
+            if (mb) nb = 32 * bh + 31 - __clz(mb);
+            if (mf) end = 32 * bh + __ffs(mf) - 1;
+            if (valid && t >= nb && (end < 0 || t < end)) acc(p);
         }
-#pragma unroll
-        for (int w = 0; w < EX_F; ++w) {
-            const int t = ti + 1 + 32 * w + lane;
-            pf[w] = (t < T) ? col.at<TILE>(t) : -1.f;
-        }
-        int nb = -1;
-        {
-            unsigned m[EX_W];
-#pragma unroll
-            for (int w = 0; w < EX_W; ++w) m[w] = __ballot_sync(0xffffffffu, pb[w] >= 0.f && !pred(pb[w]));
-#pragma unroll
-            for (int w = 0; w < EX_W; ++w)
-                if (nb < 0 && m[w]) nb = ti - 1 - 32 * w - (__ffs(m[w]) - 1);
-        }
-        for (int base = ti - 1 - 32 * EX_W; base >= lo_lim && nb < 0; base -= 32 * EX_W) {     // probe strides > 32 EX_W only
-            unsigned m[EX_W];
-#pragma unroll
-            for (int w = 0; w < EX_W; ++w) {
-                const int t = base - 32 * w - lane;
-                const bool valid = t >= lo_lim;
-                const float p = valid ? col.at<TILE>(t) : 0.f;
-                m[w] = __ballot_sync(0xffffffffu, valid && !pred(p));
+        int kb = bh - 1, kf = bh + 1;                    // next block down / up
+        bool bopen = nb < 0 && 32 * bh > lo_lim;
+        bool fopen = end < 0 && 32 * kf < T;
+        bool too_long = false;
+        while (bopen || fopen) {
+            if (fopen && 32 * kf - (nb >= 0 ? nb : 32 * (kb + 1)) > span_cap) { too_long = true; skip_to = 32 * kf; break; }
+            const int tb = 32 * kb + lane, tf = 32 * kf + lane;
+            const bool vb = bopen && tb >= lo_lim, vf = fopen && tf < T;
+            const float pb = vb ? col.at<TILE>(tb) : 0.f;                    // both loads of a round are in flight together
+            const float pf = vf ? col.at<TILE>(tf) : 0.f;
+            if (bopen) {
+                const unsigned m = __ballot_sync(0xffffffffu, vb && !pred(pb));
+                if (m) nb = 32 * kb + 31 - __clz(m);
+                if (vb && tb >= nb) acc(pb);
+                bopen = nb < 0 && 32 * kb > lo_lim;
+                --kb;
             }
-#pragma unroll
-            for (int w = 0; w < EX_W; ++w)
-                if (nb < 0 && m[w]) nb = base - 32 * w - (__ffs(m[w]) - 1);
+            if (fopen) {
+                const unsigned m = __ballot_sync(0xffffffffu, vf && !pred(pf));
+                if (m) end = 32 * kf + __ffs(m) - 1;
+                if (vf && (end < 0 || tf < end)) acc(pf);
+                ++kf;
+                fopen = end < 0 && 32 * kf < T;
+            }
         }
         int start;
         if (nb >= 0) {
@@ -527,58 +544,27 @@ __global__ void __launch_bounds__(MINB > 0 ? 128 : 1024, MINB > 0 ? MINB : 1) ex
             continue;                                    // an earlier probe lies in the same run
         } else if (!a.has_prev[s]) {
             start = 0;                                   // analyze.py:382: start_min = 0
+        } else if (too_long) {
+            continue;
         } else {
-            // analyze.py:383-398: walk into the previous block, tested against the CURRENT row mean;
-            // start_min = -T + 1 is never tested itself.
+            // analyze.py:383-398: walk into the previous block (the previous unit of the same launch, or the last unit of the
+            // stream in the previous launch's buffer), tested against the CURRENT row mean; start_min = -T + 1 is never tested
+            const CellRef pcol = (a.bpl == 1 || (s % a.bpl) == 0) ? CellRef::make<TILE>(a.Sprev, a.stream_stride, s + a.bpl - 1, fi, n)
+                                                                   : CellRef::make<TILE>(a.S, a.stream_stride, s - 1, fi, n);
             const int jmax = T - 2;                      // cells last[T-1] ... last[2]
             const int jcap = min(jmax, a.max_cols + 2);
             int jf = 0;
-            for (int base = 1; base <= jcap && jf == 0; base += 32 * EX_W) {
-                unsigned m[EX_W];
-#pragma unroll
-                for (int w = 0; w < EX_W; ++w) {
-                    const int jj = base + 32 * w + lane;
-                    const bool valid = jj <= jcap;
-                    const float p = valid ? pcol.at<TILE>(T - jj) : 0.f;
-                    m[w] = __ballot_sync(0xffffffffu, valid && !pred(p));
-                }
-#pragma unroll
-                for (int w = 0; w < EX_W; ++w)
-                    if (jf == 0 && m[w]) jf = base + 32 * w + (__ffs(m[w]) - 1);
+            for (int base = 1; base <= jcap && jf == 0; base += 32) {
+                const int jj = base + lane;
+                const bool valid = jj <= jcap;
+                const float p = valid ? pcol.at<TILE>(T - jj) : 0.f;
+                const unsigned m = __ballot_sync(0xffffffffu, valid && !pred(p));
+                if (m) jf = base + (__ffs(m) - 1);
+                if (valid && (jf == 0 || jj <= jf)) acc(p);
             }
             if (jf > 0) start = -jf;
-            else if (jcap == jmax) start = -(T - 1);     // ran into start_min
+            else if (jcap == jmax) { start = -(T - 1); if (lane == 0) acc(pcol.at<TILE>(1)); }     // ran into start_min: last[1] is in the window, untested
             else continue;                               // longer than max_cols: fails the duration test
-        }
-
-        // ---- forward: first not-above cell after ti (analyze.py:401-412); the first EX_F windows are already here
-        int end = -1;
-        const int span_cap = a.max_cols + 2;             // beyond this the duration test fails anyway
-        bool too_long = false;
-        if (EX_F > 0 && ti + 1 < T) {
-            if (ti + 1 - start > span_cap) { too_long = true; skip_to = ti + 1; }
-            else {
-                unsigned m[EX_F > 0 ? EX_F : 1];
-#pragma unroll
-                for (int w = 0; w < EX_F; ++w) m[w] = __ballot_sync(0xffffffffu, pf[w] >= 0.f && !pred(pf[w]));
-#pragma unroll
-                for (int w = 0; w < EX_F; ++w)
-                    if (end < 0 && m[w]) end = ti + 1 + 32 * w + (__ffs(m[w]) - 1);
-            }
-        }
-        for (int base = ti + 1 + 32 * EX_F; base < T && end < 0 && !too_long; base += 32 * EX_W) {
-            if (base - start > span_cap) { too_long = true; skip_to = base; break; }
-            unsigned m[EX_W];
-#pragma unroll
-            for (int w = 0; w < EX_W; ++w) {
-                const int t = base + 32 * w + lane;
-                const bool valid = t < T;
-                const float p = valid ? col.at<TILE>(t) : 0.f;
-                m[w] = __ballot_sync(0xffffffffu, valid && !pred(p));
-            }
-#pragma unroll
-            for (int w = 0; w < EX_W; ++w)
-                if (end < 0 && m[w]) end = base + 32 * w + (__ffs(m[w]) - 1);
         }
         if (too_long || end < 0) {                       // end == T: dropped, re-found from the next block
             if (!too_long) skip_to = T;
@@ -588,30 +574,7 @@ __global__ void __launch_bounds__(MINB > 0 ? 128 : 1024, MINB > 0 ? MINB : 1) ex
         const int cols = end - start + (start < 0 ? 1 : 0);
         if (cols < a.min_cols || cols > a.max_cols) continue;
 
-        // ---- statistics over data = [start, end) (analyze.py:436-447): one pass, float64 sums
         const int cnt = end - start;
-        float mx = 0.f;
-        double sum = 0.0, sdb = 0.0, sdb2 = 0.0;
-        for (int i0 = start + lane; i0 < end; i0 += 32 * EX_W) {
-            float pv[EX_W];
-#pragma unroll
-            for (int w = 0; w < EX_W; ++w) {
-                const int i = i0 + 32 * w;
-                pv[w] = i >= end ? -1.f : (i < 0 ? pcol.at<TILE>(T + i) : col.at<TILE>(i));
-            }
-#pragma unroll
-            for (int w = 0; w < EX_W; ++w)
-                if (pv[w] >= 0.f) {
-                    mx = fmaxf(mx, pv[w]);
-                    sum += (double)pv[w];
-                    // dB of one cell in float (MUFU.LG2: ~1e-6 dB absolute error, the record tolerance is 5e-4 dB); the sums stay
-                    // float64.  A float64 log10 costs ~100 instructions per cell -- a third of this kernel, which shares its
-                    // issue slots with the spectrogram of the next launch.
-                    const double db = (double)(3.0102999566398120f * __log2f(pv[w]));
-                    sdb += db;
-                    sdb2 += db * db;
-                }
-        }
         mx = warp_max(mx);
         sum = warp_sum(sum);
         sdb = warp_sum(sdb);
@@ -657,6 +620,7 @@ struct rt_engine {
     bool own_stream = false;
     int n = 0, T = 0, n_streams = 0, bpl = 1, n_units = 0, n_chunks = 0, chunk_segs = 0, n_probes = 0;
     size_t block_bytes = 0;
+    int max_work = 0;                        // capacity of d_work
     int max_records = 0;                     // effective capacity of one launch's record list
     bool reg256 = false;                     // nperseg 256: register kernel (v7n) or tensor-core kernel
     bool tc256 = false;                      // tensor-core stage 1 (spectro_tc256.cuh), TILE layout
@@ -698,7 +662,7 @@ struct rt_engine {
     cudaStream_t h2d_stream = nullptr;
     cudaEvent_t h2d_done[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr};
     unsigned long long h2d_seq = 0;
-    uint2* d_work = nullptr;
+    uint4* d_work = nullptr;
     // results ring: up to RT_SLOTS launches may be in flight before their records are fetched
     int* d_counters = nullptr;              // [slot][2]
     rt_record* d_rec[RT_SLOTS] = {nullptr, nullptr};
@@ -939,7 +903,8 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     }
     CUE(cudaMalloc(&e->d_thr, e->n_units * sizeof(float)));
     CUE(cudaMalloc(&e->d_hasprev, e->n_units * sizeof(int)));
-    CUE(cudaMalloc(&e->d_work, max_work * sizeof(uint2)));
+    CUE(cudaMalloc(&e->d_work, max_work * sizeof(uint4)));
+    e->max_work = (int)std::min<size_t>(max_work, 0x7fffffff);
     CUE(cudaMalloc(&e->d_counters, 2 * RT_SLOTS * sizeof(int)));
     CUE(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
 
@@ -971,9 +936,9 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
         CUE(cudaFuncSetAttribute(probe_lean_kernel<LAYOUT_PERM>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUE(cudaFuncSetAttribute(probe_lean_kernel<LAYOUT_LINEAR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUE(cudaFuncSetAttribute(probe_lean_kernel<LAYOUT_TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        CUE(cudaFuncSetAttribute(extract_kernel<LAYOUT_PERM, 16, 1, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        CUE(cudaFuncSetAttribute(extract_kernel<LAYOUT_LINEAR, 16, 1, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        CUE(cudaFuncSetAttribute(extract_kernel<LAYOUT_TILE, 16, 1, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CUE(cudaFuncSetAttribute(extract2_kernel<LAYOUT_PERM, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CUE(cudaFuncSetAttribute(extract2_kernel<LAYOUT_LINEAR, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CUE(cudaFuncSetAttribute(extract2_kernel<LAYOUT_TILE, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     }
     CUE(cudaMallocHost(&e->h_counters, 2 * sizeof(int)));
     CUE(cudaMemcpy(e->d_win, hwin.data(), n * sizeof(float), cudaMemcpyHostToDevice));
@@ -998,6 +963,10 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     } else {
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7n<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
         CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7n<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+#ifdef RT_LAB
+        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7m<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
+        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7m<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+#endif
     }
 #undef CUE
     *out = e;
@@ -1034,6 +1003,14 @@ int rt_engine_shape(const rt_engine* e, int32_t* n_streams, int32_t* nperseg, in
     if (T) *T = e->T;
     return RT_OK;
 }
+
+#ifdef RT_LAB
+// tools/ only (tools/build_lab_lib.sh, never the shipped library): leave scan kernels out to time what each one costs the step
+extern "C" { int rt_lab_skip = 0; int rt_lab_lean_per_sm = 0; int rt_lab_extract_per_sm = 0; int rt_lab_v7m = 0; }      // skip: bit 0 row means, bit 1 probe, bit 2 extraction; lean CTAs per SM (0 = default)
+#define RT_LAB_SKIP(b) (rt_lab_skip & (b))
+#else
+#define RT_LAB_SKIP(b) 0
+#endif
 
 int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size_t stream_stride_bytes) {
     if (!e || !iq) return fail(RT_ERR_INVALID, "null argument");
@@ -1117,6 +1094,10 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
         ta.store = 1; ta.dbg = 0; ta.prof = nullptr;
         rt::spectro_tc256_k<2><<<e->tc_grid, 512, rt::Tc256<2>::SMEM, st>>>(ta);
     } else if (use_reg) {
+#ifdef RT_LAB
+        if (rt_lab_v7m) rt::spectro_reg256_v7m<true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
+        else
+#endif
         rt::spectro_reg256_v7n<true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
     } else if (e->r16 && aligned) {
         if (e->n == 4096) rt::spectro_r16_k<4096><<<grid, 256, rt::R16Cfg<4096>::SMEM, st>>>(sa);
@@ -1141,9 +1122,12 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     CU(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), sc_st));
     if (evs) CU(cudaEventRecord(evs->ev[2], sc_st));
     const bool lean = e->scan_lean;
+#ifdef RT_LAB
+    if (rt_lab_lean_per_sm > 0) e->lean_ctas = 148 * rt_lab_lean_per_sm;
+#endif
     // the r16 kernel leaves one partial row per CTA: its n_chunks is the number of partial rows per unit either way
     const bool sep_mean = !(use_reg && e->tc256) && (lean || e->n_chunks > 48);
-    if (sep_mean) {
+    if (sep_mean && !RT_LAB_SKIP(1)) {
         row_mean_kernel<<<dim3((4 * e->n + 127) / 128, e->n_units), 128, 0, sc_st>>>(e->d_part[slot], e->d_avg[slot], e->n, e->n_chunks, e->T, (use_reg && !e->tc256) ? 1 : 0);
         CU(cudaGetLastError());
     }
@@ -1158,7 +1142,7 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     sc.n = e->n; sc.T = e->T; sc.stride = e->cfg.probe_stride; sc.n_probes = e->n_probes;
     sc.min_cols = e->cfg.min_cols; sc.max_cols = e->cfg.max_cols;
     sc.n_streams_scan = e->n_units;
-    sc.work = e->d_work; sc.counters = d_cnt; sc.rec = e->d_rec[slot]; sc.max_records = e->max_records;
+    sc.work = e->d_work; sc.max_work = e->max_work; sc.counters = d_cnt; sc.rec = e->d_rec[slot]; sc.max_records = e->max_records;
     const int pbins = std::min(e->n, 256);
     const int ppt = e->probe_ppt;
     dim3 pgrid(((e->n + pbins - 1) / pbins) * ((e->n_probes + ppt - 1) / ppt), e->n_units);
@@ -1169,7 +1153,8 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
         else if (ppt == 16) probe_kernel<L, 16><<<pgrid, pbins, 0, sc_st>>>(sc);           \
         else probe_kernel<L, 32><<<pgrid, pbins, 0, sc_st>>>(sc);                          \
     } while (0)
-    if (use_reg && e->tc256) RT_PROBE(LAYOUT_TILE);
+    if (RT_LAB_SKIP(2)) {}
+    else if (use_reg && e->tc256) RT_PROBE(LAYOUT_TILE);
     else if (use_reg) RT_PROBE(LAYOUT_PERM);
     else RT_PROBE(LAYOUT_LINEAR);
 #undef RT_PROBE
@@ -1177,12 +1162,17 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     if (evs) CU(cudaEventRecord(evs->ev[4], sc_st));
     // full size: one wave of 128-thread CTAs, four 32-cell windows per round trip; lean: one 32-cell window, no speculative
     // forward fetch (fewest sectors: the kernel runs beside the spectrogram of the next launch)
+    int ex_ctas = e->lean_ctas;
+#ifdef RT_LAB
+    if (rt_lab_extract_per_sm > 0) ex_ctas = 148 * rt_lab_extract_per_sm;
+#endif
 #define RT_EXTRACT(L)                                                                      \
     do {                                                                                   \
-        if (lean) extract_kernel<L, 16, 1, 0><<<e->lean_ctas, 128, 0, sc_st>>>(sc);        \
-        else extract_kernel<L, 0><<<148 * 24, 128, 0, sc_st>>>(sc);                        \
+        if (lean) extract2_kernel<L, 16><<<ex_ctas, 128, 0, sc_st>>>(sc);                  \
+        else extract2_kernel<L, 8><<<148 * 24, 128, 0, sc_st>>>(sc);                       \
     } while (0)
-    if (use_reg && e->tc256) RT_EXTRACT(LAYOUT_TILE);
+    if (RT_LAB_SKIP(4)) {}
+    else if (use_reg && e->tc256) RT_EXTRACT(LAYOUT_TILE);
     else if (use_reg) RT_EXTRACT(LAYOUT_PERM);
     else RT_EXTRACT(LAYOUT_LINEAR);
 #undef RT_EXTRACT

@@ -66,8 +66,9 @@ __device__ __forceinline__ void stg128_hint(float4* dst, float4 v, uint64_t pol)
 //   * inter-pass twiddles as (wr, wi) scalars: the lane swap / sign live in FFMA2 operand modifiers
 //   * invalid (ragged-tail) lanes masked by a 0/1 factor in the row-sum FMA instead of a branch
 // ---------------------------------------------------------------------------------------------
-struct R256v7 {
-    static constexpr int WARPS = 4, THREADS = 128, STAGES = 4, MINB = 4;
+template <int WARPS_, int MINB_>
+struct R256v7T {
+    static constexpr int WARPS = WARPS_, THREADS = 32 * WARPS_, STAGES = 4, MINB = MINB_;
     static constexpr int RAW_STRIDE = 544, XROW = 36, XTILE = 16 * XROW;
     static constexpr int STAGE_BYTES = 2 * RAW_STRIDE;                  // two segments per warp per round
     static constexpr int RAW_BYTES = WARPS * STAGES * STAGE_BYTES;
@@ -78,6 +79,7 @@ struct R256v7 {
     static constexpr int SMEM = TAB_OFF + 2048 + 1024;
     static constexpr int SEGS_PER_ROUND = 2 * WARPS;
 };
+using R256v7 = R256v7T<4, 4>;
 
 __device__ __forceinline__ bool elect_one() {
     unsigned ok;
@@ -160,9 +162,8 @@ __device__ __forceinline__ void lane_byte_sums_alu(uint32_t addr, unsigned& sI, 
 // T64: time-blocked S layout [t / 64][position / 8][t % 64][position % 8] instead of [t][position]: the 64 time steps of a group
 // of 8 row positions are 2 KB of contiguous memory, so the scan kernels' walks along time read consecutive sectors (whole
 // 128-byte lines, open DRAM rows) instead of one sector out of every 1 KB row.
-template <bool STORE, bool HINT, bool TWS, bool WINS, bool ALUSUM, bool PROBE = false, int T64 = 0, bool PIN = false, bool PACC = false>
+template <bool STORE, bool HINT, bool TWS, bool WINS, bool ALUSUM, bool PROBE = false, int T64 = 0, bool PIN = false, bool PACC = false, class C = R256v7>
 __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
-    using C = R256v7;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     const int tid = threadIdx.x;
     const int lane = tid & 31, h = lane >> 4, j = lane & 15;
@@ -385,6 +386,13 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
 // addresses pinned in registers (see PIN in spectro_reg256_v7_body)
 template <bool STORE>
 __global__ void __launch_bounds__(R256v7::THREADS, 4) spectro_reg256_v7n(SpectroArgs a) {
+    spectro_reg256_v7_body<STORE, false, false, false, false, false, 0, true>(a);
+}
+
+// the same body capped at 112 registers: 4 CTAs x 128 threads x 112 = 57344 registers leave 8192 of an SM's 65536 free, room
+// for TWO 32-register scan CTAs beside the resident spectrogram CTAs instead of one (see rt_engine.cu, lean schedule)
+template <bool STORE>
+__global__ void __maxnreg__(112) spectro_reg256_v7m(SpectroArgs a) {
     spectro_reg256_v7_body<STORE, false, false, false, false, false, 0, true>(a);
 }
 

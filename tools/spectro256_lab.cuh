@@ -318,4 +318,11 @@ __global__ void __launch_bounds__(R256v7::THREADS, 4) spectro_reg256_v7p(Spectro
     spectro_reg256_v7_body<STORE, false, false, false, false, true>(a);
 }
 
+
+// v7n with W warps per CTA and MB resident CTAs per SM (the body is generic in the warp count): how many warps per SM does the
+// 118-register body want?  W = 1: 17 x 120 registers fit the register file where 4-warp CTAs stop at 16 warps.
+template <bool STORE, int W, int MB>
+__global__ void __launch_bounds__(32 * W, MB) spectro_reg256_v7w(SpectroArgs a) {
+    spectro_reg256_v7_body<STORE, false, false, false, false, false, 0, true, false, R256v7T<W, MB>>(a);
+}
 }  // namespace rt

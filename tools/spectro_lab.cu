@@ -18,6 +18,7 @@ using namespace rt;
 static const char* g_filter = nullptr;
 static cudaStream_t g_st[4];
 static int g_nst = 1;
+static int g_pipe = 0;
 
 struct Ctx {
     int streams, T, reps;
@@ -65,6 +66,18 @@ void run_k(Ctx& c, kern_t kern, int THREADS, int SMEM, const char* name, int chu
     };
     for (int i = 0; i < 2; ++i) launch();
     CK(cudaDeviceSynchronize());
+    float pipe_us = -1.f;
+    if (g_pipe > 0 && group <= 0) {      // steady state: `g_pipe` launches back to back, alternating between two streams (the engine's schedule)
+        cudaEvent_t f0, j1; CK(cudaEventCreateWithFlags(&f0, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&j1, cudaEventDisableTiming));
+        CK(cudaEventRecord(e0, g_st[0]));
+        CK(cudaEventRecord(f0, g_st[0])); CK(cudaStreamWaitEvent(g_st[1], f0, 0));
+        for (int i = 0; i < g_pipe; ++i) kern<<<dim3(a.n_chunks, c.streams), THREADS, SMEM, g_st[i & 1]>>>(a);
+        CK(cudaEventRecord(j1, g_st[1])); CK(cudaStreamWaitEvent(g_st[0], j1, 0));
+        CK(cudaEventRecord(e1, g_st[0]));
+        CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        pipe_us = 1e3f * ms / g_pipe;
+    }
     float best = 1e9f, tot = 0;
     for (int i = 0; i < c.reps; ++i) {
         CK(cudaEventRecord(e0, g_st[0]));
@@ -97,8 +110,8 @@ void run_k(Ctx& c, kern_t kern, int THREADS, int SMEM, const char* name, int chu
         CK(cudaMemset(c.d_S + ((size_t)(c.streams - 1) * c.T + c.T - 16) * 256, 0, sv.size() * 4));
     }
     const double samples = (double)c.streams * c.T * 256;
-    printf("%-34s chunk %4d grp %2d regs %3d occ %d smem %6d  mean %8.2f us  best %8.2f us  %7.1f GB/s  rowsum maxrel %.2e  S maxrel %.2e\n",
-           name, chunk, group, fa.numRegs, occ, SMEM, 1e3 * tot / c.reps, 1e3 * best, 2 * samples / (best * 1e-3) / 1e9, maxrel, smax);
+    printf("%-34s chunk %4d grp %2d regs %3d occ %2d smem %6d  mean %8.2f us  best %8.2f us  %7.1f GB/s  pipelined %7.2f us  rowsum maxrel %.2e  S maxrel %.2e\n",
+           name, chunk, group, fa.numRegs, occ, SMEM, 1e3 * tot / c.reps, 1e3 * best, 2 * samples / (best * 1e-3) / 1e9, pipe_us, maxrel, smax);
     fflush(stdout);
 }
 
@@ -111,6 +124,7 @@ int main(int argc, char** argv) {
     c.streams = argc > 1 ? atoi(argv[1]) : 64;
     c.reps = argc > 2 ? atoi(argv[2]) : 10;
     g_filter = argc > 3 ? argv[3] : nullptr;
+    g_pipe = argc > 4 ? atoi(argv[4]) : 0;
     const int block = 2400000;
     c.T = block / 256;
     c.stride = (size_t)2 * block;
@@ -156,6 +170,19 @@ int main(int argc, char** argv) {
     using S2   = R256Cfg<1, 1, 4, 4, 2, true,  false, 1, false>;
     using S6   = R256Cfg<1, 1, 4, 4, 6, true,  false, 1, false>;
 
+#define RUNW(W, MB, CH) run_k(c, spectro_reg256_v7w<true, W, MB>, 32 * W, R256v7T<W, MB>::SMEM, "v7w W" #W " MB" #MB, CH)
+    run_k(c, spectro_reg256_v7n<true>, R256v7::THREADS, R256v7::SMEM, "v7n", 192);
+    run_k(c, spectro_reg256_v7m<true>, R256v7::THREADS, R256v7::SMEM, "v7m (112 regs)", 192);
+    RUNW(4, 4, 192);
+    RUNW(2, 8, 96);
+    RUNW(2, 9, 96);
+    RUNW(1, 16, 48);
+    RUNW(1, 17, 48);
+    RUNW(1, 18, 48);
+    RUNW(1, 19, 48);
+    RUNW(1, 17, 96);
+    RUNW(1, 18, 96);
+    RUNW(2, 9, 192);
     run<V6>(c, "v6 (baseline)", 256);
     run<V6n>(c, "v6 no S store", 256);
     run_k(c, spectro_reg256_v7<true>, R256v7::THREADS, R256v7::SMEM, "v7", 256);
