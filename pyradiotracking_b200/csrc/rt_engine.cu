@@ -80,9 +80,11 @@ struct CellRef {
         return c;
     }
     template <int L>
-    __device__ __forceinline__ float at(int t) const {
-        return L == LAYOUT_TILE ? base[(size_t)(t >> 5) * 8192 + (size_t)(t & 31) * 4] : base[(size_t)t * step];
+    __device__ __forceinline__ const float* ptr(int t) const {
+        return L == LAYOUT_TILE ? base + ((size_t)(t >> 5) * 8192 + (size_t)(t & 31) * 4) : base + (size_t)t * step;
     }
+    template <int L>
+    __device__ __forceinline__ float at(int t) const { return *ptr<L>(t); }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -257,6 +259,9 @@ struct ScanArgs {
     uint4* work;           // (stream << 16 | fi, ti | (chain members - 1) << 24, row mean, threshold): consecutive probe columns ti, ti + stride, ...;
                            // the two floats save the extraction warp two dependent round trips in front of its first cells
     int max_work;          // capacity of the work list (worst case: every probe column of every bin)
+#ifdef RT_LAB
+    int lab_mode;          // tools/ timing experiments (wrong results): bit 0 no statistics, bit 2 first block only
+#endif
     int* counters;         // [0] work items, [1] records
     rt_record* rec;
     int max_records;
@@ -493,6 +498,9 @@ __global__ void __launch_bounds__(128, MINB) extract2_kernel(ScanArgs a) {
         float mx = 0.f;
         double sum = 0.0, sdb = 0.0, sdb2 = 0.0;
         auto acc = [&](float p) {
+#ifdef RT_LAB
+            if (a.lab_mode & 1) { mx = fmaxf(mx, p); return; }
+#endif
             mx = fmaxf(mx, p);
             sum += (double)p;
             // dB of one cell in float (MUFU.LG2: ~1e-6 dB absolute error, the record tolerance is 5e-4 dB); the sums stay float64
@@ -516,6 +524,9 @@ __global__ void __launch_bounds__(128, MINB) extract2_kernel(ScanArgs a) {
         bool bopen = nb < 0 && 32 * bh > lo_lim;
         bool fopen = end < 0 && 32 * kf < T;
         bool too_long = false;
+#ifdef RT_LAB
+        if (a.lab_mode & 4) { bopen = fopen = false; if (end < 0) end = ti + 1; if (nb < 0) nb = max(ti - 1, 0); }
+#endif
         while (bopen || fopen) {
             if (fopen && 32 * kf - (nb >= 0 ? nb : 32 * (kb + 1)) > span_cap) { too_long = true; skip_to = 32 * kf; break; }
             const int tb = 32 * kb + lane, tf = 32 * kf + lane;
@@ -1006,7 +1017,7 @@ int rt_engine_shape(const rt_engine* e, int32_t* n_streams, int32_t* nperseg, in
 
 #ifdef RT_LAB
 // tools/ only (tools/build_lab_lib.sh, never the shipped library): leave scan kernels out to time what each one costs the step
-extern "C" { int rt_lab_skip = 0; int rt_lab_lean_per_sm = 0; int rt_lab_extract_per_sm = 0; int rt_lab_v7m = 0; }      // skip: bit 0 row means, bit 1 probe, bit 2 extraction; lean CTAs per SM (0 = default)
+extern "C" { int rt_lab_extract_mode = 0; int rt_lab_skip = 0; int rt_lab_lean_per_sm = 0; int rt_lab_extract_per_sm = 0; int rt_lab_v7m = 0; }      // skip: bit 0 row means, bit 1 probe, bit 2 extraction; lean CTAs per SM (0 = default)
 #define RT_LAB_SKIP(b) (rt_lab_skip & (b))
 #else
 #define RT_LAB_SKIP(b) 0
@@ -1142,6 +1153,9 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     sc.n = e->n; sc.T = e->T; sc.stride = e->cfg.probe_stride; sc.n_probes = e->n_probes;
     sc.min_cols = e->cfg.min_cols; sc.max_cols = e->cfg.max_cols;
     sc.n_streams_scan = e->n_units;
+#ifdef RT_LAB
+    sc.lab_mode = rt_lab_extract_mode;
+#endif
     sc.work = e->d_work; sc.max_work = e->max_work; sc.counters = d_cnt; sc.rec = e->d_rec[slot]; sc.max_records = e->max_records;
     const int pbins = std::min(e->n, 256);
     const int ppt = e->probe_ppt;
@@ -1164,6 +1178,7 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     // forward fetch (fewest sectors: the kernel runs beside the spectrogram of the next launch)
     int ex_ctas = e->lean_ctas;
 #ifdef RT_LAB
+    if (rt_lab_extract_mode & 2) sc.stream_stride = 0;     // every unit's walk reads unit 0's S (19 MB: stays in L2)
     if (rt_lab_extract_per_sm > 0) ex_ctas = 148 * rt_lab_extract_per_sm;
 #endif
 #define RT_EXTRACT(L)                                                                      \
