@@ -60,12 +60,19 @@ __device__ __forceinline__ bool above(float p, float thr, float avg, float snr) 
 
 // Spectrogram layouts.
 //   LINEAR (generic kernel)        S[stream][t][bin]
-//   PERM   (register kernel v7)    S[stream][t][pos(bin)], pos = 64 (k2 >> 2) + 4 k1 + (k2 & 3) for bin = k1 + 16 k2: thread k1 of a
-//                                  half-warp stores its bins as four float4, each store instruction 256 contiguous bytes
+//   PERM   (register kernel v7)    S[stream][t / TG][pos(bin) / 4][t % TG][pos % 4], pos = 64 (k2 >> 2) + 4 k1 + (k2 & 3) for bin = k1 + 16 k2:
+//                                  thread k1 of a half-warp stores its bins as four float4; with TG = 2 the half-warps of a warp (time
+//                                  steps t, t + 1) fill 512 contiguous bytes per store instruction and a walk along time finds two
+//                                  cells per 32-byte sector
 //   TILE   (tensor-core kernel)    S[stream][t / 32][quad][t % 32][4], quad = 4 k1 + (k2 >> 2) (rt::tile_cell_off): a thread owns a
 //                                  segment, a warp stores 512 contiguous bytes, 32 time steps of a bin lie within 512 bytes
 // (time-blocked variants of PERM were measured and rejected: DESIGN.md 5.7)
 enum { LAYOUT_LINEAR = 0, LAYOUT_PERM = 1, LAYOUT_TILE = 2 };
+// PERM time group (spectro256.cuh, TG): S[stream][t / TG][pos / 4][t % TG][pos % 4]
+#ifndef RT_PERM_TG
+#define RT_PERM_TG 2
+#endif
+constexpr int PERM_TG = RT_PERM_TG;
 __host__ __device__ constexpr bool layout_is_perm(int L) { return L == LAYOUT_PERM; }
 
 struct CellRef {
@@ -75,13 +82,19 @@ struct CellRef {
     __device__ __forceinline__ static CellRef make(const float* S, size_t stream_stride, int s, int fi, int n) {
         CellRef c;
         if (L == LAYOUT_TILE) { c.base = S + (size_t)s * stream_stride + (size_t)((fi & 15) * 4 + (fi >> 6)) * 128 + ((fi >> 4) & 3); c.step = 0; }
-        else if (L == LAYOUT_PERM) { c.base = S + (size_t)s * stream_stride + (((fi >> 6) << 6) | ((fi & 15) << 2) | ((fi >> 4) & 3)); c.step = 256; }
+        else if (L == LAYOUT_PERM) {
+            const int pos = ((fi >> 6) << 6) | ((fi & 15) << 2) | ((fi >> 4) & 3);
+            c.base = S + (size_t)s * stream_stride + (pos >> 2) * (4 * PERM_TG) + (pos & 3);
+            c.step = 256;
+        }
         else { c.base = S + (size_t)s * stream_stride + fi; c.step = n; }
         return c;
     }
     template <int L>
     __device__ __forceinline__ const float* ptr(int t) const {
-        return L == LAYOUT_TILE ? base + ((size_t)(t >> 5) * 8192 + (size_t)(t & 31) * 4) : base + (size_t)t * step;
+        return L == LAYOUT_TILE ? base + ((size_t)(t >> 5) * 8192 + (size_t)(t & 31) * 4)
+             : (L == LAYOUT_PERM && PERM_TG > 1) ? base + ((size_t)(t / PERM_TG) * (256 * PERM_TG) + (size_t)(t % PERM_TG) * 4)
+                                                 : base + (size_t)t * step;
     }
     template <int L>
     __device__ __forceinline__ float at(int t) const { return *ptr<L>(t); }
@@ -794,7 +807,7 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     if (cfg->scan_schedule < RT_SCAN_AUTO || cfg->scan_schedule > RT_SCAN_LEAN) return fail(RT_ERR_INVALID, "unknown scan_schedule");
     if (cfg->launch_streams < 0 || cfg->launch_streams > 2) return fail(RT_ERR_INVALID, "launch_streams must be 0 (auto), 1 or 2");
     if (cfg->launch_streams == 2 && cfg->scan_schedule == RT_SCAN_SERIAL) return fail(RT_ERR_INVALID, "two launch streams need an overlapped scan schedule");
-    if (cfg->chunk_segs < 0 || cfg->chunk_segs % 8 != 0) return fail(RT_ERR_INVALID, "chunk_segs must be 0 (auto) or a multiple of 8");
+    if (cfg->chunk_segs < 0 || cfg->chunk_segs % (PERM_TG > 2 ? 4 * PERM_TG : 8) != 0) return fail(RT_ERR_INVALID, "chunk_segs must be 0 (auto) or a multiple of 8");
     if (cfg->fft_impl == RT_FFT_TC256 && bpl != 1) return fail(RT_ERR_INVALID, "RT_FFT_TC256 does not take blocks_per_launch > 1");
     for (int r : cfg->reserved) if (r != 0) return fail(RT_ERR_INVALID, "rt_config.reserved must be zero");
 
@@ -845,7 +858,9 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
         e->n_chunks = std::min(resident, (e->T + teams - 1) / teams);
         e->chunk_segs = (e->T + e->n_chunks - 1) / e->n_chunks;      // informational
     }
-    e->s_stride = e->tc256 ? (size_t)((e->T + 31) / 32) * 8192 : (size_t)e->T * n;
+    e->s_stride = e->tc256 ? (size_t)((e->T + 31) / 32) * 8192
+                : e->reg256 ? (size_t)((e->T + PERM_TG - 1) / PERM_TG) * PERM_TG * n      // PERM: whole time groups
+                            : (size_t)e->T * n;
     const size_t max_work = (size_t)e->n_units * n * e->n_probes;    // every probe cell a hit: the work list cannot overflow
     // every record belongs to a different probe hit, so max_work records is the worst case; capped at 4 Mi (160 MB per slot)
     e->max_records = cfg->max_records > 0 ? cfg->max_records : (int)std::min<size_t>(max_work, (size_t)4 << 20);
@@ -972,12 +987,8 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
         const size_t smem = (size_t)n * (2 * sizeof(float2) + sizeof(float)) + 16;
         CUE(cudaFuncSetAttribute(spectro_generic<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     } else {
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7n<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7n<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-#ifdef RT_LAB
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7m<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM));
-        CUE(cudaFuncSetAttribute(rt::spectro_reg256_v7m<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-#endif
+        CUE((cudaFuncSetAttribute(rt::spectro_reg256_v7n<true, PERM_TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R256v7::SMEM)));
+        CUE((cudaFuncSetAttribute(rt::spectro_reg256_v7n<true, PERM_TG>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)));
     }
 #undef CUE
     *out = e;
@@ -1017,7 +1028,7 @@ int rt_engine_shape(const rt_engine* e, int32_t* n_streams, int32_t* nperseg, in
 
 #ifdef RT_LAB
 // tools/ only (tools/build_lab_lib.sh, never the shipped library): leave scan kernels out to time what each one costs the step
-extern "C" { int rt_lab_extract_mode = 0; int rt_lab_skip = 0; int rt_lab_lean_per_sm = 0; int rt_lab_extract_per_sm = 0; int rt_lab_v7m = 0; }      // skip: bit 0 row means, bit 1 probe, bit 2 extraction; lean CTAs per SM (0 = default)
+extern "C" { int rt_lab_extract_mode = 0; int rt_lab_skip = 0; int rt_lab_lean_per_sm = 0; int rt_lab_extract_per_sm = 0; }      // skip: bit 0 row means, bit 1 probe, bit 2 extraction; lean CTAs per SM (0 = default)
 #define RT_LAB_SKIP(b) (rt_lab_skip & (b))
 #else
 #define RT_LAB_SKIP(b) 0
@@ -1105,11 +1116,7 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
         ta.store = 1; ta.dbg = 0; ta.prof = nullptr;
         rt::spectro_tc256_k<2><<<e->tc_grid, 512, rt::Tc256<2>::SMEM, st>>>(ta);
     } else if (use_reg) {
-#ifdef RT_LAB
-        if (rt_lab_v7m) rt::spectro_reg256_v7m<true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
-        else
-#endif
-        rt::spectro_reg256_v7n<true><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
+        rt::spectro_reg256_v7n<true, PERM_TG><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
     } else if (e->r16 && aligned) {
         if (e->n == 4096) rt::spectro_r16_k<4096><<<grid, 256, rt::R16Cfg<4096>::SMEM, st>>>(sa);
         else rt::spectro_r16_k<1024><<<grid, 256, rt::R16Cfg<1024>::SMEM, st>>>(sa);

@@ -162,8 +162,19 @@ __device__ __forceinline__ void lane_byte_sums_alu(uint32_t addr, unsigned& sI, 
 // T64: time-blocked S layout [t / 64][position / 8][t % 64][position % 8] instead of [t][position]: the 64 time steps of a group
 // of 8 row positions are 2 KB of contiguous memory, so the scan kernels' walks along time read consecutive sectors (whole
 // 128-byte lines, open DRAM rows) instead of one sector out of every 1 KB row.
-template <bool STORE, bool HINT, bool TWS, bool WINS, bool ALUSUM, bool PROBE = false, int T64 = 0, bool PIN = false, bool PACC = false, class C = R256v7>
+// TG (time group, 1 / 2 / 4 / 8): S layout [t / TG][position / 4][t % TG][position % 4] -- the 16-byte granule (4 bins) of TG consecutive
+// time steps lie side by side, so a walk along time (the extraction kernel) finds 2 cells per 32-byte sector at TG = 2, 4 per 64
+// bytes at TG = 4, 8 per 128-byte line at TG = 8 instead of one sector per cell.  TG = 2 costs this kernel nothing: the two half-warps
+// of a warp hold time steps t and t + 1, and a store instruction of the warp is 512 contiguous bytes.  TG > 2 deals groups of TG
+// consecutive segments to a warp (TG / 2 rounds per group) so that the sectors of a group are completed by one warp within microseconds.
+template <bool STORE, bool HINT, bool TWS, bool WINS, bool ALUSUM, bool PROBE = false, int T64 = 0, bool PIN = false, bool PACC = false, class C = R256v7, int TG = 1>
 __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
+    static_assert(TG == 1 || TG == 2 || TG == 4 || TG == 8, "time group");
+    static_assert(TG == 1 || (!PROBE && T64 == 0), "probe plane / time-blocked lab layouts are TG = 1 only");
+    constexpr int RPG = TG > 2 ? TG / 2 : 1;              // rounds per group of TG segments
+    constexpr int GSEGS = C::WARPS * (TG > 2 ? TG : 2);    // segments the CTA covers per RPG rounds
+    // segment (of half-warp 0) of round `it` of this warp, relative to its first one
+    auto seg_rel = [](int it) { return TG > 2 ? (it / RPG) * GSEGS + 2 * (it % RPG) : it * C::SEGS_PER_ROUND; };
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     const int tid = threadIdx.x;
     const int lane = tid & 31, h = lane >> 4, j = lane & 15;
@@ -171,8 +182,14 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
     const int s = blockIdx.y;
     const int seg0 = blockIdx.x * a.chunk_segs;
     const int seg1 = min(a.T, seg0 + a.chunk_segs);
-    const int first = seg0 + 2 * warp;
-    const int n_it = (seg1 - first + C::SEGS_PER_ROUND - 1) / C::SEGS_PER_ROUND;   // warp-uniform
+    const int first = seg0 + (TG > 2 ? TG : 2) * warp;
+    int n_it;                                                                        // warp-uniform
+    if (TG > 2) {
+        const int R = seg1 - 1 - first;                   // rounds whose first segment exists
+        n_it = R < 0 ? 0 : (R / GSEGS) * RPG + min(RPG, (R % GSEGS) / 2 + 1);
+    } else {
+        n_it = (seg1 - first + C::SEGS_PER_ROUND - 1) / C::SEGS_PER_ROUND;
+    }
 
     const uint32_t sm0 = smem_u32(dyn_smem);
     const uint32_t wraw = sm0 + warp * (C::STAGES * C::STAGE_BYTES);
@@ -197,8 +214,8 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
     uint64_t pol_in = 0, pol_out = 0;
     if (HINT) { pol_in = policy_evict_first(); pol_out = PIN ? policy_evict_first() : policy_evict_last(); }   // v7h (HINT + PIN): S stores evict-first (streaming)
     auto issue = [&](int itx, int st) {                              // executed by one elected lane
-        const int sg = first + C::SEGS_PER_ROUND * itx;
-        const uint8_t* p0 = gsrc + (size_t)itx * (C::SEGS_PER_ROUND * 512);
+        const int sg = first + seg_rel(itx);
+        const uint8_t* p0 = gsrc + (size_t)seg_rel(itx) * 512;
         const uint8_t* p1 = (sg + 1 <= last_seg) ? p0 + 512 : p0;   // ragged tail: copy the same segment twice
         const uint32_t bar = wbar + 8 * st, dst = wraw + st * C::STAGE_BYTES;
         mbar_expect_tx_a(bar, 1024);
@@ -264,13 +281,15 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
         mbar_wait(wbar, 0);
         cm = detrend_of(my_sum_);
     }
-    float* sdst = a.S + (size_t)s * a.S_stream_stride + (size_t)(first + h) * 256 + 4 * j;   // += 8 * 256 floats per round
+    // TG = 1: row (first + h), 4 j floats in; TG = 2: row pair first / 2 (first is even), granule j of 8 floats, half h of it
+    float* sdst = a.S + (size_t)s * a.S_stream_stride + (TG == 2 ? (size_t)first * 256 + 8 * j + 4 * h : (size_t)(first + h) * 256 + 4 * j);   // += 8 * 256 floats per round
+    float* const sbaseTG = a.S + (size_t)s * a.S_stream_stride + (4 * TG) * j;                // TG > 2: + (seg / TG) * 256 TG + (seg % TG) * 4
     // T64 = positions per block (8 or 32): [t / 64][pos / T64][t % 64][pos % T64]; this thread's positions are 64 c + 4 j ...
     float* const sbase64 = a.S + (size_t)s * a.S_stream_stride + (T64 ? ((4 * j) / (T64 ? T64 : 1)) * (64 * T64) + (4 * j) % (T64 ? T64 : 1) : 0);
     uint32_t st_off = 0, st_bar = wbar;
     unsigned phase = 0;
-    const uint8_t* g_next = gsrc + (size_t)C::STAGES * (C::SEGS_PER_ROUND * 512);   // source of the next round to be issued
-    int sg_next = first + C::STAGES * C::SEGS_PER_ROUND;
+    const uint8_t* g_next = gsrc + (size_t)seg_rel(C::STAGES) * 512;               // source of the next round to be issued
+    int sg_next = first + seg_rel(C::STAGES);
     int seg = first + h;
     // probe plane: seg = pq * probe_stride + prem, kept incrementally (seg advances by SEGS_PER_ROUND per round)
     int pq = 0, prem = 0;
@@ -299,8 +318,14 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
                 }
             } else if (elect_one()) issue(it + C::STAGES, it % C::STAGES);
         }
-        g_next += C::SEGS_PER_ROUND * 512;
-        sg_next += C::SEGS_PER_ROUND;
+        if (TG > 2) {
+            const int d = seg_rel(it + C::STAGES + 1) - seg_rel(it + C::STAGES);
+            g_next += d * 512;
+            sg_next += d;
+        } else {
+            g_next += C::SEGS_PER_ROUND * 512;
+            sg_next += C::SEGS_PER_ROUND;
+        }
         // advance to the next stage; its byte sums overlap the butterflies below
         st_off += C::STAGE_BYTES; st_bar += 8;
         if (st_off == C::STAGES * C::STAGE_BYTES) { st_off = 0; st_bar = wbar; phase ^= 1; }
@@ -343,12 +368,14 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
         }
         if (STORE) {
             if (valid) {
-                float4* dst = T64 ? reinterpret_cast<float4*>(sbase64 + ((size_t)(seg >> 6) << 14) + (seg & 63) * T64) : reinterpret_cast<float4*>(sdst);
+                float4* dst = T64 ? reinterpret_cast<float4*>(sbase64 + ((size_t)(seg >> 6) << 14) + (seg & 63) * T64)
+                            : TG > 2 ? reinterpret_cast<float4*>(sbaseTG + (size_t)(seg / TG) * (256 * TG) + (seg % TG) * 4)
+                                     : reinterpret_cast<float4*>(sdst);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const float4 o = make_float4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
                     if (HINT) stg128_hint(dst + 16 * c, o, pol_out);
-                    else dst[(T64 ? 1024 : 16) * c] = o;          // 64 positions further: 64 * 64 floats in either blocked layout
+                    else dst[(T64 ? 1024 : 16 * TG) * c] = o;     // 64 positions further (T64: 64 * 64 floats in either blocked layout)
                 }
             }
             sdst += C::SEGS_PER_ROUND * 256;
@@ -362,7 +389,7 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
                 while (prem >= a.probe_stride) { prem -= a.probe_stride; ++pq; }
             }
         }
-        seg += C::SEGS_PER_ROUND;
+        seg += TG > 2 ? seg_rel(it + 1) - seg_rel(it) : C::SEGS_PER_ROUND;
         cm = cm_next;
     }
 
@@ -384,16 +411,9 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
 }
 
 // addresses pinned in registers (see PIN in spectro_reg256_v7_body)
-template <bool STORE>
+template <bool STORE, int TG = 1>
 __global__ void __launch_bounds__(R256v7::THREADS, 4) spectro_reg256_v7n(SpectroArgs a) {
-    spectro_reg256_v7_body<STORE, false, false, false, false, false, 0, true>(a);
-}
-
-// the same body capped at 112 registers: 4 CTAs x 128 threads x 112 = 57344 registers leave 8192 of an SM's 65536 free, room
-// for TWO 32-register scan CTAs beside the resident spectrogram CTAs instead of one (see rt_engine.cu, lean schedule)
-template <bool STORE>
-__global__ void __maxnreg__(112) spectro_reg256_v7m(SpectroArgs a) {
-    spectro_reg256_v7_body<STORE, false, false, false, false, false, 0, true>(a);
+    spectro_reg256_v7_body<STORE, false, false, false, false, false, 0, true, false, R256v7, TG>(a);
 }
 
 }  // namespace rt

@@ -22,8 +22,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--streams", type=int, default=64)
+    ap.add_argument("--lib", default="librtb200_lab.so", help="lab build under tools/ (RT_LAB_DEFS=-DRT_PERM_TG=4 sh tools/build_lab_lib.sh tg4 -> librtb200_lab_tg4.so)")
     ap.add_argument("--extract-mode", type=int, nargs="*", default=[0], help="bit 0: no statistics, bit 1: walks read an L2-resident S, bit 2: first block only")
-    ap.add_argument("--v7m", type=int, default=0, help="1: the 112-register spectrogram kernel")
     ap.add_argument("--extract-per-sm", type=int, nargs="*", default=[0])
     ap.add_argument("--lean-per-sm", type=int, nargs="*", default=[0], help="lean scan CTAs per SM to sweep (0 = the engine's default)")
     args = ap.parse_args()
@@ -33,11 +33,10 @@ def main():
     from pyradiotracking_b200.analyze import BatchAnalyzer
     from tools.bench_configs import run
 
-    build.LIB = os.path.join(ROOT, "tools", "librtb200_lab.so")
+    build.LIB = os.path.join(ROOT, "tools", args.lib)
     lib = engine.load_library()
     skip = ctypes.c_int.in_dll(lib, "rt_lab_skip")
     lean = ctypes.c_int.in_dll(lib, "rt_lab_lean_per_sm")
-    ctypes.c_int.in_dll(lib, "rt_lab_v7m").value = args.v7m
     exps = ctypes.c_int.in_dll(lib, "rt_lab_extract_per_sm")
     xmode = ctypes.c_int.in_dll(lib, "rt_lab_extract_mode")
     for per_sm, ex_sm, xm in [(p, x, m) for p in args.lean_per_sm for x in args.extract_per_sm for m in args.extract_mode]:
@@ -51,7 +50,7 @@ def main():
             skip.value = mask
             run(name, getattr(synth, args.workload), args.streams, args.steps, args.warmup, torch, synth, BatchAnalyzer, kernel_timing=0)
         d = json.loads(buf.getvalue().strip().splitlines()[-1])
-        print(json.dumps({"variant": name, "skip_mask": mask, "v7m": args.v7m, "lean_ctas_per_sm": per_sm, "extract_ctas_per_sm": ex_sm, "extract_mode": xm, "ms_per_step": d["ms_per_step"]}), flush=True)
+        print(json.dumps({"variant": name, "skip_mask": mask, "lean_ctas_per_sm": per_sm, "extract_ctas_per_sm": ex_sm, "extract_mode": xm, "ms_per_step": d["ms_per_step"]}), flush=True)
 
 
 if __name__ == "__main__":

@@ -145,7 +145,7 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&c.d_win, 1024)); CK(cudaMalloc(&c.d_tw, 2048));
     CK(cudaMemcpy(c.d_win, win.data(), 1024, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c.d_tw, tw.data(), 2048, cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&c.d_S, (size_t)c.streams * c.T * 256 * 4));
+    CK(cudaMalloc(&c.d_S, ((size_t)c.streams * c.T + 64) * 256 * 4));
     c.part_elems = (size_t)c.streams * 1024 * 256;
     CK(cudaMalloc(&c.d_part, c.part_elems * 4));
 
@@ -172,7 +172,9 @@ int main(int argc, char** argv) {
 
 #define RUNW(W, MB, CH) run_k(c, spectro_reg256_v7w<true, W, MB>, 32 * W, R256v7T<W, MB>::SMEM, "v7w W" #W " MB" #MB, CH)
     run_k(c, spectro_reg256_v7n<true>, R256v7::THREADS, R256v7::SMEM, "v7n", 192);
-    run_k(c, spectro_reg256_v7m<true>, R256v7::THREADS, R256v7::SMEM, "v7m (112 regs)", 192);
+    run_k(c, spectro_reg256_v7n<true, 2>, R256v7::THREADS, R256v7::SMEM, "v7n TG2", 192);
+    run_k(c, spectro_reg256_v7n<true, 4>, R256v7::THREADS, R256v7::SMEM, "v7n TG4", 192);
+    run_k(c, spectro_reg256_v7n<true, 8>, R256v7::THREADS, R256v7::SMEM, "v7n TG8", 192);
     RUNW(4, 4, 192);
     RUNW(2, 8, 96);
     RUNW(2, 9, 96);
