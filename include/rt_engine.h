@@ -38,7 +38,7 @@ enum {
 
 /* fft_impl selector: which spectrogram kernel runs (tests compare them). */
 enum {
-    RT_FFT_AUTO = 0,      /* nperseg 256: RT_FFT_REG256, otherwise RT_FFT_GENERIC */
+    RT_FFT_AUTO = 0,      /* nperseg 256: RT_FFT_REG256; 1024 / 4096: radix-16 Stockham kernel (spectro_r16.cuh); otherwise RT_FFT_GENERIC */
     RT_FFT_GENERIC = 1,   /* shared-memory Stockham FFT, any power-of-two nperseg */
     RT_FFT_REG256 = 2,    /* nperseg 256: 16x16 FFT in registers (packed fp32x2), TMA-fed */
     RT_FFT_TC256 = 3      /* nperseg 256, boxcar/hann/hamming: first FFT stage on the tensor cores (tcgen05, fp16 x split-fp16 -> fp32) */

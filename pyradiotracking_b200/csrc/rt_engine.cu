@@ -31,6 +31,9 @@
 #include "spectro256.cuh"
 #include "spectro_tc256.cuh"
 #include "spectro_r16.cuh"
+#ifdef RT_LAB
+#include "../../tools/spectro_s256_lab.cuh"      // 256-point-core kernel for nperseg 1024 / 4096: measured, not adopted (profiles/r02_s256_kernel.txt)
+#endif
 
 namespace {
 
@@ -66,14 +69,24 @@ __device__ __forceinline__ bool above(float p, float thr, float avg, float snr) 
 //                                  cells per 32-byte sector
 //   TILE   (tensor-core kernel)    S[stream][t / 32][quad][t % 32][4], quad = 4 k1 + (k2 >> 2) (rt::tile_cell_off): a thread owns a
 //                                  segment, a warp stores 512 contiguous bytes, 32 time steps of a bin lie within 512 bytes
+//   PERMR  (spectro_s256, n = 256 R) S[stream][t][256 k2 + pos(k1)] for bin = R k1 + k2, pos() as in PERM: half-warp k2 of a team stores the
+//                                  bins of its 256-point sub-transform, 256 contiguous bytes per store instruction
 // (time-blocked variants of PERM were measured and rejected: DESIGN.md 5.7)
-enum { LAYOUT_LINEAR = 0, LAYOUT_PERM = 1, LAYOUT_TILE = 2 };
+enum { LAYOUT_LINEAR = 0, LAYOUT_PERM = 1, LAYOUT_TILE = 2, LAYOUT_PERMR = 3 };
 // PERM time group (spectro256.cuh, TG): S[stream][t / TG][pos / 4][t % TG][pos % 4]
 #ifndef RT_PERM_TG
 #define RT_PERM_TG 2
 #endif
 constexpr int PERM_TG = RT_PERM_TG;
-__host__ __device__ constexpr bool layout_is_perm(int L) { return L == LAYOUT_PERM; }
+__host__ __device__ constexpr int perm256(int k) { return ((k >> 6) << 6) | ((k & 15) << 2) | ((k >> 4) & 3); }                // bin -> position
+__host__ __device__ constexpr int unperm256(int p) { return ((p >> 2) & 15) + 16 * (4 * (p >> 6) + (p & 3)); }                 // position -> bin
+// row position -> FFT bin for the layouts whose rows are not in bin order (n = bins per row)
+template <int L>
+__device__ __forceinline__ int pos_to_bin(int idx, int n) {
+    if (L == LAYOUT_PERM) return unperm256(idx);
+    if (L == LAYOUT_PERMR) return (n >> 8) * unperm256(idx & 255) + (idx >> 8);
+    return idx;
+}
 
 struct CellRef {
     const float* base;     // stream base + the bin's constant part
@@ -87,6 +100,7 @@ struct CellRef {
             c.base = S + (size_t)s * stream_stride + (pos >> 2) * (4 * PERM_TG) + (pos & 3);
             c.step = 256;
         }
+        else if (L == LAYOUT_PERMR) { const int R = n >> 8; c.base = S + (size_t)s * stream_stride + 256 * (fi & (R - 1)) + perm256(fi / R); c.step = n; }
         else { c.base = S + (size_t)s * stream_stride + fi; c.step = n; }
         return c;
     }
@@ -272,6 +286,7 @@ struct ScanArgs {
     uint4* work;           // (stream << 16 | fi, ti | (chain members - 1) << 24, row mean, threshold): consecutive probe columns ti, ti + stride, ...;
                            // the two floats save the extraction warp two dependent round trips in front of its first cells
     int max_work;          // capacity of the work list (worst case: every probe column of every bin)
+    int widen;             // extraction: widen the forward walk after three round trips (small launches)
 #ifdef RT_LAB
     int lab_mode;          // tools/ timing experiments (wrong results): bit 0 no statistics, bit 2 first block only
 #endif
@@ -308,7 +323,8 @@ __global__ void probe_kernel(ScanArgs a) {
     // PERM layout: the thread index is the position inside the S row (and inside the chunk-sum rows, which the register
     // kernel writes in the same order), so a warp reads 128 contiguous bytes per load instead of 2 floats out of each of
     // 8 sectors; position 64 a + 4 k1 + b holds bin k1 + 16 (4 a + b)
-    auto bin_of = [](int ix) { return layout_is_perm(TILE) ? ((ix >> 2) & 15) + 16 * (4 * (ix >> 6) + (ix & 3)) : ix; };
+    const int n_bins = a.n;
+    auto bin_of = [n_bins](int ix) { return pos_to_bin<TILE>(ix, n_bins); };
     const int fi = bin_of(idx);
     const float thr = a.thr[s], snr = a.snr;
     if (tid == 0) s_n = 0;
@@ -412,7 +428,7 @@ __global__ void __launch_bounds__(128, 16) probe_lean_kernel(ScanArgs a) {
         const int pb = tile % npb, g = (tile / npb) % ngr, s = tile / (npb * ngr);
         const int idx = pb * 32 + lane;
         if (idx >= a.n) continue;
-        const int fi = layout_is_perm(TILE) ? ((idx >> 2) & 15) + 16 * (4 * (idx >> 6) + (idx & 3)) : idx;
+        const int fi = pos_to_bin<TILE>(idx, a.n);
         const CellRef col = CellRef::make<TILE>(a.S, a.stream_stride, s, fi, a.n);
         float c0[LEAN_PPT];
 #pragma unroll
@@ -540,12 +556,22 @@ __global__ void __launch_bounds__(128, MINB) extract2_kernel(ScanArgs a) {
 #ifdef RT_LAB
         if (a.lab_mode & 4) { bopen = fopen = false; if (end < 0) end = ti + 1; if (nb < 0) nb = max(ti - 1, 0); }
 #endif
+        // forward blocks per round trip: 1, 1, 1, then (a.widen: small launches, where the chain of round trips IS the kernel time and
+        // the sectors cost nothing) 2, 2, 4, 4, ... -- a 25-block pulse of a 20 MS/s stream takes 9 round trips instead of 25
+        int rounds = 0;
         while (bopen || fopen) {
             if (fopen && 32 * kf - (nb >= 0 ? nb : 32 * (kb + 1)) > span_cap) { too_long = true; skip_to = 32 * kf; break; }
-            const int tb = 32 * kb + lane, tf = 32 * kf + lane;
-            const bool vb = bopen && tb >= lo_lim, vf = fopen && tf < T;
-            const float pb = vb ? col.at<TILE>(tb) : 0.f;                    // both loads of a round are in flight together
-            const float pf = vf ? col.at<TILE>(tf) : 0.f;
+            const int wf = !a.widen || rounds < 3 ? 1 : (rounds < 5 ? 2 : 4);
+            ++rounds;
+            const int tb = 32 * kb + lane;
+            const bool vb = bopen && tb >= lo_lim;
+            const float pb = vb ? col.at<TILE>(tb) : 0.f;                    // every load of a round is in flight together
+            float pf[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const int tf = 32 * (kf + w) + lane;
+                pf[w] = (fopen && w < wf && tf < T) ? col.at<TILE>(tf) : -1.f;
+            }
             if (bopen) {
                 const unsigned m = __ballot_sync(0xffffffffu, vb && !pred(pb));
                 if (m) nb = 32 * kb + 31 - __clz(m);
@@ -554,10 +580,16 @@ __global__ void __launch_bounds__(128, MINB) extract2_kernel(ScanArgs a) {
                 --kb;
             }
             if (fopen) {
-                const unsigned m = __ballot_sync(0xffffffffu, vf && !pred(pf));
-                if (m) end = 32 * kf + __ffs(m) - 1;
-                if (vf && (end < 0 || tf < end)) acc(pf);
-                ++kf;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    if (w < wf && end < 0) {
+                        const int tf = 32 * (kf + w) + lane;
+                        const unsigned m = __ballot_sync(0xffffffffu, pf[w] >= 0.f && !pred(pf[w]));
+                        if (m) end = 32 * (kf + w) + __ffs(m) - 1;
+                        if (pf[w] >= 0.f && (end < 0 || tf < end)) acc(pf[w]);
+                    }
+                }
+                kf += wf;
                 fopen = end < 0 && 32 * kf < T;
             }
         }
@@ -620,13 +652,13 @@ __global__ void __launch_bounds__(128, MINB) extract2_kernel(ScanArgs a) {
     }
 }
 
-// PERM / TILE -> [T][256] for the parity hook, with the power scale of the tensor-core path undone (a power of two: exact)
+// PERM / TILE / PERMR -> [T][n] for the parity hook, with the power scale of the tensor-core path undone (a power of two: exact)
 template <int L>
-__global__ void untile_kernel(const float* S, float* out, int total, float inv_scale) {
+__global__ void untile_kernel(const float* S, float* out, int total, int n, float inv_scale) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    const int t = idx >> 8, fi = idx & 255;
-    out[idx] = CellRef::make<L>(S, 0, 0, fi, 256).at<L>(t) * inv_scale;
+    const int t = idx / n, fi = idx % n;
+    out[idx] = CellRef::make<L>(S, 0, 0, fi, n).template at<L>(t) * inv_scale;
 }
 
 }  // namespace
@@ -634,6 +666,14 @@ __global__ void untile_kernel(const float* S, float* out, int total, float inv_s
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+#ifdef RT_LAB
+// tools/ only (tools/build_lab_lib.sh, never the shipped library): leave scan kernels out to time what each one costs the step
+extern "C" { int rt_lab_extract_mode = 0; int rt_lab_skip = 0; int rt_lab_lean_per_sm = 0; int rt_lab_extract_per_sm = 0; int rt_lab_s256 = 0; }      // skip: bit 0 row means, bit 1 probe, bit 2 extraction; lean CTAs per SM (0 = default)
+#define RT_LAB_SKIP(b) (rt_lab_skip & (b))
+#else
+#define RT_LAB_SKIP(b) 0
+#endif
+
 // error text for the other translation units of the library (rt_matcher.cpp)
 int rt_internal_fail(int code, const char* msg) { return fail(code, msg); }
 
@@ -649,6 +689,8 @@ struct rt_engine {
     bool reg256 = false;                     // nperseg 256: register kernel (v7n) or tensor-core kernel
     bool tc256 = false;                      // tensor-core stage 1 (spectro_tc256.cuh), TILE layout
     bool r16 = false;                        // nperseg 1024 / 4096: radix-16 Stockham kernel (spectro_r16.cuh), LINEAR layout
+    bool s256 = false;                       // lab builds only: 256-point-core kernel (tools/spectro_s256_lab.cuh), PERMR layout
+    int last_layout = LAYOUT_LINEAR;         // S layout of the latest launch (rt_engine_read_spectrogram)
     size_t s_stride = 0;                     // floats per unit in a spectrogram buffer
     float pscale = 1.f;                      // power factor carried by S / row means / thresholds (tensor-core path), a power of two
     uint4* d_bmat = nullptr;                 // tensor-core operand image
@@ -833,6 +875,9 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     e->reg256 = (n == 256) && (cfg->fft_impl != RT_FFT_GENERIC);
     e->tc256 = cfg->fft_impl == RT_FFT_TC256;
     e->r16 = (n == 1024 || n == 4096) && cfg->fft_impl == RT_FFT_AUTO;
+#ifdef RT_LAB
+    if (e->r16 && rt_lab_s256) { e->r16 = false; e->s256 = true; }
+#endif
     e->chunk_segs = 32;
     if (e->reg256) {
         // short blocks (300 kS/s SDRs, replay): shorter chunks = more CTAs per unit.  The choice depends on T only, so a
@@ -850,10 +895,10 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
         }
     }
     e->n_chunks = (e->T + e->chunk_segs - 1) / e->chunk_segs;
-    if (e->r16) {
-        // segments are dealt round-robin over n_chunks CTAs (x teams) per unit: 148 SMs x the resident CTAs (3 at 1024, 2 at 4096)
+    if (e->r16 || e->s256) {
+        // segments are dealt round-robin over n_chunks CTAs (x teams) per unit: 148 SMs x the resident CTAs (r16: 3 at 1024, 2 at 4096)
         const int teams = n == 4096 ? 1 : 4;
-        const int resident = 148 * (n == 4096 ? rt::R16Cfg<4096>::CTAS_PER_SM : rt::R16Cfg<1024>::CTAS_PER_SM);
+        const int resident = 148 * (e->s256 ? 2 : n == 4096 ? rt::R16Cfg<4096>::CTAS_PER_SM : rt::R16Cfg<1024>::CTAS_PER_SM);
         // (depends on T only, like chunk_segs above: the same row means alone and inside a batch)
         e->n_chunks = std::min(resident, (e->T + teams - 1) / teams);
         e->chunk_segs = (e->T + e->n_chunks - 1) / e->n_chunks;      // informational
@@ -962,6 +1007,10 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
         CUE(cudaFuncSetAttribute(probe_lean_kernel<LAYOUT_PERM>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUE(cudaFuncSetAttribute(probe_lean_kernel<LAYOUT_LINEAR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUE(cudaFuncSetAttribute(probe_lean_kernel<LAYOUT_TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+#ifdef RT_LAB
+        CUE(cudaFuncSetAttribute(probe_lean_kernel<LAYOUT_PERMR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CUE((cudaFuncSetAttribute(extract2_kernel<LAYOUT_PERMR, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)));
+#endif
         CUE(cudaFuncSetAttribute(extract2_kernel<LAYOUT_PERM, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUE(cudaFuncSetAttribute(extract2_kernel<LAYOUT_LINEAR, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUE(cudaFuncSetAttribute(extract2_kernel<LAYOUT_TILE, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -983,6 +1032,12 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
         if (n == 4096) CUE(cudaFuncSetAttribute(rt::spectro_r16_k<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R16Cfg<4096>::SMEM));
         else CUE(cudaFuncSetAttribute(rt::spectro_r16_k<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::R16Cfg<1024>::SMEM));
     }
+#ifdef RT_LAB
+    if (e->s256) {
+        if (n == 4096) CUE(cudaFuncSetAttribute(rt::spectro_s256_k<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::S256Cfg<4096>::SMEM));
+        else CUE(cudaFuncSetAttribute(rt::spectro_s256_k<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::S256Cfg<1024>::SMEM));
+    }
+#endif
     if (!e->reg256) {
         const size_t smem = (size_t)n * (2 * sizeof(float2) + sizeof(float)) + 16;
         CUE(cudaFuncSetAttribute(spectro_generic<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1026,13 +1081,6 @@ int rt_engine_shape(const rt_engine* e, int32_t* n_streams, int32_t* nperseg, in
     return RT_OK;
 }
 
-#ifdef RT_LAB
-// tools/ only (tools/build_lab_lib.sh, never the shipped library): leave scan kernels out to time what each one costs the step
-extern "C" { int rt_lab_extract_mode = 0; int rt_lab_skip = 0; int rt_lab_lean_per_sm = 0; int rt_lab_extract_per_sm = 0; }      // skip: bit 0 row means, bit 1 probe, bit 2 extraction; lean CTAs per SM (0 = default)
-#define RT_LAB_SKIP(b) (rt_lab_skip & (b))
-#else
-#define RT_LAB_SKIP(b) 0
-#endif
 
 int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size_t stream_stride_bytes) {
     if (!e || !iq) return fail(RT_ERR_INVALID, "null argument");
@@ -1117,6 +1165,11 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
         rt::spectro_tc256_k<2><<<e->tc_grid, 512, rt::Tc256<2>::SMEM, st>>>(ta);
     } else if (use_reg) {
         rt::spectro_reg256_v7n<true, PERM_TG><<<grid, rt::R256v7::THREADS, rt::R256v7::SMEM, st>>>(sa);
+#ifdef RT_LAB
+    } else if (e->s256 && aligned) {
+        if (e->n == 4096) rt::spectro_s256_k<4096><<<grid, 256, rt::S256Cfg<4096>::SMEM, st>>>(sa);
+        else rt::spectro_s256_k<1024><<<grid, 256, rt::S256Cfg<1024>::SMEM, st>>>(sa);
+#endif
     } else if (e->r16 && aligned) {
         if (e->n == 4096) rt::spectro_r16_k<4096><<<grid, 256, rt::R16Cfg<4096>::SMEM, st>>>(sa);
         else rt::spectro_r16_k<1024><<<grid, 256, rt::R16Cfg<1024>::SMEM, st>>>(sa);
@@ -1163,6 +1216,7 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
 #ifdef RT_LAB
     sc.lab_mode = rt_lab_extract_mode;
 #endif
+    sc.widen = ((long long)e->n_units * e->T < 300000) ? 1 : 0;
     sc.work = e->d_work; sc.max_work = e->max_work; sc.counters = d_cnt; sc.rec = e->d_rec[slot]; sc.max_records = e->max_records;
     const int pbins = std::min(e->n, 256);
     const int ppt = e->probe_ppt;
@@ -1174,9 +1228,14 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
         else if (ppt == 16) probe_kernel<L, 16><<<pgrid, pbins, 0, sc_st>>>(sc);           \
         else probe_kernel<L, 32><<<pgrid, pbins, 0, sc_st>>>(sc);                          \
     } while (0)
+    const int layout = use_reg ? (e->tc256 ? LAYOUT_TILE : LAYOUT_PERM) : (e->s256 && aligned) ? LAYOUT_PERMR : LAYOUT_LINEAR;
+    e->last_layout = layout;
     if (RT_LAB_SKIP(2)) {}
-    else if (use_reg && e->tc256) RT_PROBE(LAYOUT_TILE);
-    else if (use_reg) RT_PROBE(LAYOUT_PERM);
+    else if (layout == LAYOUT_TILE) RT_PROBE(LAYOUT_TILE);
+    else if (layout == LAYOUT_PERM) RT_PROBE(LAYOUT_PERM);
+#ifdef RT_LAB
+    else if (layout == LAYOUT_PERMR) RT_PROBE(LAYOUT_PERMR);
+#endif
     else RT_PROBE(LAYOUT_LINEAR);
 #undef RT_PROBE
     CU(cudaGetLastError());
@@ -1194,8 +1253,11 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
         else extract2_kernel<L, 8><<<148 * 24, 128, 0, sc_st>>>(sc);                       \
     } while (0)
     if (RT_LAB_SKIP(4)) {}
-    else if (use_reg && e->tc256) RT_EXTRACT(LAYOUT_TILE);
-    else if (use_reg) RT_EXTRACT(LAYOUT_PERM);
+    else if (layout == LAYOUT_TILE) RT_EXTRACT(LAYOUT_TILE);
+    else if (layout == LAYOUT_PERM) RT_EXTRACT(LAYOUT_PERM);
+#ifdef RT_LAB
+    else if (layout == LAYOUT_PERMR) RT_EXTRACT(LAYOUT_PERMR);
+#endif
     else RT_EXTRACT(LAYOUT_LINEAR);
 #undef RT_EXTRACT
     CU(cudaGetLastError());
@@ -1311,11 +1373,19 @@ int rt_engine_read_spectrogram(rt_engine* e, int32_t stream, float* out) {
     if (e->scan_stream) CU(cudaStreamSynchronize(e->scan_stream));
     if (e->reg256) {
         if (!e->d_tmp) CU(cudaMalloc(&e->d_tmp, cells * sizeof(float)));
-        if (e->tc256) untile_kernel<LAYOUT_TILE><<<(unsigned)((cells + 255) / 256), 256, 0, e->stream>>>(src, e->d_tmp, (int)cells, 1.f / e->pscale);
-        else untile_kernel<LAYOUT_PERM><<<(unsigned)((cells + 255) / 256), 256, 0, e->stream>>>(src, e->d_tmp, (int)cells, 1.f);
+        if (e->tc256) untile_kernel<LAYOUT_TILE><<<(unsigned)((cells + 255) / 256), 256, 0, e->stream>>>(src, e->d_tmp, (int)cells, 256, 1.f / e->pscale);
+        else untile_kernel<LAYOUT_PERM><<<(unsigned)((cells + 255) / 256), 256, 0, e->stream>>>(src, e->d_tmp, (int)cells, 256, 1.f);
         CU(cudaGetLastError());
         src = e->d_tmp;
     }
+#ifdef RT_LAB
+    else if (e->last_layout == LAYOUT_PERMR) {
+        if (!e->d_tmp) CU(cudaMalloc(&e->d_tmp, cells * sizeof(float)));
+        untile_kernel<LAYOUT_PERMR><<<(unsigned)((cells + 255) / 256), 256, 0, e->stream>>>(src, e->d_tmp, (int)cells, e->n, 1.f);
+        CU(cudaGetLastError());
+        src = e->d_tmp;
+    }
+#endif
     CU(cudaMemcpyAsync(out, src, cells * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return RT_OK;
