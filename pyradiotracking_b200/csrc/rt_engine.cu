@@ -498,7 +498,7 @@ __device__ __forceinline__ float warp_max(float v) {
 //   * max / sum / sum dB / sum dB^2 are accumulated while the blocks pass through the registers -- no second pass over the
 //     run, which was 150 of the ~340 sectors of a typical 150-column pulse;
 //   * one fixed per-lane order of the float64 sums, so every schedule returns the same bits.
-template <int TILE, int MINB>
+template <int TILE, int MINB, int WF = 1>
 __global__ void __launch_bounds__(128, MINB) extract2_kernel(ScanArgs a) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -556,19 +556,21 @@ __global__ void __launch_bounds__(128, MINB) extract2_kernel(ScanArgs a) {
 #ifdef RT_LAB
         if (a.lab_mode & 4) { bopen = fopen = false; if (end < 0) end = ti + 1; if (nb < 0) nb = max(ti - 1, 0); }
 #endif
-        // forward blocks per round trip: 1, 1, 1, then (a.widen: small launches, where the chain of round trips IS the kernel time and
-        // the sectors cost nothing) 2, 2, 4, 4, ... -- a 25-block pulse of a 20 MS/s stream takes 9 round trips instead of 25
+        // forward blocks per round trip: 1, 1, 1, then (WF = 4 and a.widen: small launches, where the chain of round trips IS the kernel
+        // time and the sectors cost nothing) 2, 2, 4, 4, ... -- a 25-block pulse of a 20 MS/s stream takes 9 round trips instead of 25.
+        // The lean instantiation (WF = 1) keeps one block per direction: beside the spectrogram every sector counts and 32 registers
+        // have no room for more loads in flight.
         int rounds = 0;
         while (bopen || fopen) {
             if (fopen && 32 * kf - (nb >= 0 ? nb : 32 * (kb + 1)) > span_cap) { too_long = true; skip_to = 32 * kf; break; }
-            const int wf = !a.widen || rounds < 3 ? 1 : (rounds < 5 ? 2 : 4);
+            const int wf = WF == 1 || !a.widen || rounds < 3 ? 1 : (rounds < 5 ? 2 : 4);
             ++rounds;
             const int tb = 32 * kb + lane;
             const bool vb = bopen && tb >= lo_lim;
             const float pb = vb ? col.at<TILE>(tb) : 0.f;                    // every load of a round is in flight together
-            float pf[4];
+            float pf[WF];
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
+            for (int w = 0; w < WF; ++w) {
                 const int tf = 32 * (kf + w) + lane;
                 pf[w] = (fopen && w < wf && tf < T) ? col.at<TILE>(tf) : -1.f;
             }
@@ -581,7 +583,7 @@ __global__ void __launch_bounds__(128, MINB) extract2_kernel(ScanArgs a) {
             }
             if (fopen) {
 #pragma unroll
-                for (int w = 0; w < 4; ++w) {
+                for (int w = 0; w < WF; ++w) {
                     if (w < wf && end < 0) {
                         const int tf = 32 * (kf + w) + lane;
                         const unsigned m = __ballot_sync(0xffffffffu, pf[w] >= 0.f && !pred(pf[w]));
@@ -1250,6 +1252,7 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
 #define RT_EXTRACT(L)                                                                      \
     do {                                                                                   \
         if (lean) extract2_kernel<L, 16><<<ex_ctas, 128, 0, sc_st>>>(sc);                  \
+        else if (sc.widen) extract2_kernel<L, 8, 4><<<148 * 24, 128, 0, sc_st>>>(sc);      \
         else extract2_kernel<L, 8><<<148 * 24, 128, 0, sc_st>>>(sc);                       \
     } while (0)
     if (RT_LAB_SKIP(4)) {}
