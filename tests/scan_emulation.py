@@ -1,8 +1,9 @@
-"""CPU emulation of the device scan algorithm (pyradiotracking_b200/csrc/rt_engine.cu: probe kernels + extract_kernel).
+"""CPU emulation of the device scan algorithm (pyradiotracking_b200/csrc/rt_engine.cu: probe kernels + extract2_kernel).
 
 Test infrastructure: it restates, in plain Python over a boolean "above" matrix, WHAT the CUDA kernels decide --
 probe hits, the quick +-PROBE_QUICK resolution, chaining of consecutive surviving hits into one work item, the member
-loop with `skip_to`, the windowed backward / carry / forward walks with their early exits, the coarse duration gate --
+loop with `skip_to`, the block-wise walks down and up from the probe column with their early exits, the carry walk, the coarse
+duration gate --
 so that the schedule can be checked against the reference's sequential loop (oracle.restatement.extract_sequential,
 analyze.py:354-433) on random patterns without a GPU.  The kernels' arithmetic (predicate, statistics) is not emulated.
 """
@@ -57,26 +58,64 @@ def probe_items(ab: np.ndarray, T: int, stride: int, min_cols: int, ppt: int) ->
 
 
 def extract_item(ab: np.ndarray, ab_prev: Optional[np.ndarray], T: int, stride: int, min_cols: int, max_cols: int,
-                 ti0: int, members: int, ex_w: int, ex_f: int) -> List[Tuple[int, int]]:
-    """(start, end) records of one work item: extract_kernel's member loop."""
+                 ti0: int, members: int, widen: bool = False) -> List[Tuple[int, int]]:
+    """(start, end) records of one work item: extract2_kernel's member loop -- aligned 32-column blocks, the probe's own block
+    first, then one block down and `wf` blocks up per round trip while that side of the run is open, the span cap evaluated on
+    what is known so far, the carry walk into the previous block."""
     out = []
     skip_to = 0
+    span_cap = max_cols + 2
     for mem in range(members):
         ti = ti0 + mem * stride
         if ti < skip_to:
             continue
         lo_lim = max(ti - stride, 0)
-        nb = -1
-        for t in range(ti - 1, lo_lim - 1, -1):            # nearest not-above cell in [lo_lim, ti)
-            if not ab[t]:
-                nb = t
+        bh = ti >> 5
+
+        def not_above(b, lo, hi):                        # not-above columns of block b inside [lo, hi)
+            return [t for t in range(max(32 * b, lo), min(32 * b + 32, hi)) if not ab[t]]
+
+        nb = end = -1
+        own = not_above(bh, lo_lim, T)
+        below, beyond = [t for t in own if t < ti], [t for t in own if t > ti]
+        if below:
+            nb = max(below)
+        if beyond:
+            end = min(beyond)
+        kb, kf = bh - 1, bh + 1
+        bopen = nb < 0 and 32 * bh > lo_lim
+        fopen = end < 0 and 32 * kf < T
+        too_long = False
+        rounds = 0
+        while bopen or fopen:
+            if fopen and 32 * kf - (nb if nb >= 0 else 32 * (kb + 1)) > span_cap:
+                too_long = True
+                skip_to = 32 * kf
                 break
+            wf = 1 if (not widen or rounds < 3) else (2 if rounds < 5 else 4)
+            rounds += 1
+            if bopen:
+                c = not_above(kb, lo_lim, T)
+                if c:
+                    nb = max(c)
+                bopen = nb < 0 and 32 * kb > lo_lim
+                kb -= 1
+            if fopen:
+                for w in range(wf):
+                    if end < 0:
+                        c = not_above(kf + w, 0, T)
+                        if c:
+                            end = min(c)
+                kf += wf
+                fopen = end < 0 and 32 * kf < T
         if nb >= 0:
             start = nb
         elif ti - stride >= 0:
             continue
         elif ab_prev is None:
             start = 0
+        elif too_long:
+            continue
         else:
             jmax = T - 2
             jcap = min(jmax, max_cols + 2)
@@ -91,23 +130,6 @@ def extract_item(ab: np.ndarray, ab_prev: Optional[np.ndarray], T: int, stride: 
                 start = -(T - 1)
             else:
                 continue
-        end = -1
-        span_cap = max_cols + 2
-        too_long = False
-        base = ti + 1
-        first = True
-        while base < T and end < 0:
-            if base - start > span_cap:
-                too_long = True
-                skip_to = base
-                break
-            width = 32 * (ex_f if first else ex_w)
-            for t in range(base, min(T, base + width)):
-                if not ab[t]:
-                    end = t
-                    break
-            base += width
-            first = False
         if too_long or end < 0:
             if not too_long:
                 skip_to = T
@@ -121,14 +143,14 @@ def extract_item(ab: np.ndarray, ab_prev: Optional[np.ndarray], T: int, stride: 
 
 
 def device_scan(ab: np.ndarray, ab_prev: Optional[np.ndarray], stride: int, min_cols: int, max_cols: int,
-                ppt: int = 32, ex_w: int = 4, ex_f: int = 4) -> Set[Tuple[int, int, int]]:
+                ppt: int = 32, widen: bool = False) -> Set[Tuple[int, int, int]]:
     """All (bin, start, end) the device emits for a block; `ab` is [bins][T] booleans (predicate already applied)."""
     out = set()
     n, T = ab.shape
     for fi in range(n):
         prev = None if ab_prev is None else ab_prev[fi]
         for ti0, members in probe_items(ab[fi], T, stride, min_cols, ppt):
-            for start, end in extract_item(ab[fi], prev, T, stride, min_cols, max_cols, ti0, members, ex_w, ex_f):
+            for start, end in extract_item(ab[fi], prev, T, stride, min_cols, max_cols, ti0, members, widen):
                 assert (fi, start, end) not in out, "a run was emitted twice"
                 out.add((fi, start, end))
     return out

@@ -1,4 +1,4 @@
-"""The device scan schedule (chained work items, member loop, windowed walks, early exits) restated on the CPU
+"""The device scan schedule (chained work items, member loop, block-wise walks, early exits) restated on the CPU
 (tests/scan_emulation.py) must pick exactly the runs the reference's sequential probe loop picks (analyze.py:354-433)."""
 import numpy as np
 import pytest
@@ -20,8 +20,8 @@ def _pattern(rng, n, T, stride, density):
 
 
 @pytest.mark.parametrize("stride,min_cols,max_cols,T", [(9, 8, 49, 400), (74, 73, 377, 1500), (4, 3, 12, 97), (1, 0, 2, 40), (39, 38, 198, 900)])
-@pytest.mark.parametrize("ppt,ex_w,ex_f", [(32, 4, 4), (8, 2, 2)])
-def test_device_schedule_equals_reference_loop(stride, min_cols, max_cols, T, ppt, ex_w, ex_f):
+@pytest.mark.parametrize("ppt,widen", [(32, False), (8, True), (8, False)])
+def test_device_schedule_equals_reference_loop(stride, min_cols, max_cols, T, ppt, widen):
     rng = np.random.default_rng(1000 * stride + ppt)
     n_total = 0
     for trial in range(6):
@@ -35,7 +35,7 @@ def test_device_schedule_equals_reference_loop(stride, min_cols, max_cols, T, pp
             prev[0, :] = True
         for ab_prev in (None, prev):
             want = reference_scan(cur, ab_prev, stride, min_cols, max_cols)
-            got = device_scan(cur, ab_prev, stride, min_cols, max_cols, ppt=ppt, ex_w=ex_w, ex_f=ex_f)
+            got = device_scan(cur, ab_prev, stride, min_cols, max_cols, ppt=ppt, widen=widen)
             assert got == want
             n_total += len(want)
     assert n_total > 0
