@@ -269,7 +269,11 @@ class BatchAnalyzer:
         # shadow filter per analyzer unit (signals of one callback share ts_start, so offsets are enough): one pass over the
         # whole batch, the units shifted so far apart in time that they cannot overlap
         if len(r) > 1:
-            fin.shadow[:] = shadow_mask(fin.ts_off_us + fin.stream * _UNIT_GAP_US, fin.dur_us, fin.max)
+            # per unit in C (exact pairwise pass over the few signals of a callback, csrc/rt_pyfinal.c); a unit with thousands of
+            # candidates falls back to the O(S log S) sweep over the whole batch
+            cols = [np.ascontiguousarray(c) for c in (fin.stream, fin.ts_off_us, fin.dur_us, fin.max)]
+            if _rtfinal.shadow_units(*cols, fin.shadow.view(np.uint8)) != 0:
+                fin.shadow[:] = shadow_mask(fin.ts_off_us + fin.stream * _UNIT_GAP_US, fin.dur_us, fin.max)
         return fin
 
     def unit_ts(self, ts_start: Sequence[datetime.datetime]) -> List[datetime.datetime]:

@@ -115,7 +115,80 @@ done:
     return out;
 }
 
+
+/*
+ * shadow_units(unit, off_us, dur_us, max, out) -> 0 | 1
+ *   The shadow filter of SignalAnalyzer.filter_shadow_signals / is_shadow_of (radiotracking/analyze.py:282-328) for the signals of
+ *   many analyzer units at once: rows sorted by unit; signal i is a shadow iff a signal j of the SAME unit overlaps it in time
+ *   (closed intervals in integer microseconds: not ts_i > ts_j + dur_j, not ts_i + dur_i < ts_j) and is strictly louder.
+ *   A unit holds the detections of one callback (tens of signals, ~800 on the loudest dense fixture), so every unit is an exact
+ *   pairwise pass over its rows sorted by start time, cut off where the start times leave [ts_i - longest duration, ts_i + dur_i].
+ *   Returns 1 without touching `out` if a unit holds more than 8192 signals (the caller then uses the O(S log S) numpy sweep).
+ */
+typedef struct { int64_t ts, te; double mx; Py_ssize_t row; } shadow_row;
+static int shadow_cmp(const void *a, const void *b) {
+    const shadow_row *x = (const shadow_row *)a, *y = (const shadow_row *)b;
+    return x->ts < y->ts ? -1 : (x->ts > y->ts ? 1 : (x->row < y->row ? -1 : (x->row > y->row ? 1 : 0)));
+}
+static PyObject *shadow_units(PyObject *self, PyObject *args) {
+    PyObject *o[5];
+    if (!PyArg_ParseTuple(args, "OOOOO", &o[0], &o[1], &o[2], &o[3], &o[4])) return NULL;
+    Py_buffer b[5];
+    int nb = 0;
+    PyObject *res = NULL;
+    shadow_row *rows = NULL;
+    Py_buffer first;
+    if (PyObject_GetBuffer(o[0], &first, PyBUF_CONTIG_RO) < 0) return NULL;
+    const Py_ssize_t n = first.len / 8;
+    PyBuffer_Release(&first);
+    static const char *names[4] = {"unit", "off_us", "dur_us", "max"};
+    for (; nb < 4; ++nb)
+        if (get_buf(o[nb], &b[nb], 8, n, names[nb]) < 0) goto done;
+    if (PyObject_GetBuffer(o[4], &b[4], PyBUF_CONTIG) < 0) goto done;
+    nb = 5;
+    if (b[4].itemsize != 1 || b[4].len != n) { PyErr_SetString(PyExc_ValueError, "out: expected n bytes"); goto done; }
+    {
+        const int64_t *unit = (const int64_t *)b[0].buf, *off = (const int64_t *)b[1].buf, *dur = (const int64_t *)b[2].buf;
+        const double *mx = (const double *)b[3].buf;
+        unsigned char *out = (unsigned char *)b[4].buf;
+        Py_ssize_t longest = 0;
+        for (Py_ssize_t i = 0, j; i < n; i = j) {
+            for (j = i + 1; j < n && unit[j] == unit[i]; ++j) {}
+            if (j - i > longest) longest = j - i;
+        }
+        if (longest > 8192) { res = PyLong_FromLong(1); goto done; }
+        rows = (shadow_row *)PyMem_Malloc((size_t)(longest > 0 ? longest : 1) * sizeof(shadow_row));
+        if (!rows) { PyErr_NoMemory(); goto done; }
+        for (Py_ssize_t i = 0, j; i < n; i = j) {
+            for (j = i + 1; j < n && unit[j] == unit[i]; ++j) {}
+            const Py_ssize_t k = j - i;
+            int64_t dmax = 0;
+            for (Py_ssize_t r = 0; r < k; ++r) {
+                rows[r].ts = off[i + r]; rows[r].te = off[i + r] + dur[i + r]; rows[r].mx = mx[i + r]; rows[r].row = i + r;
+                if (dur[i + r] > dmax) dmax = dur[i + r];
+            }
+            qsort(rows, (size_t)k, sizeof(shadow_row), shadow_cmp);
+            for (Py_ssize_t r = 0; r < k; ++r) {
+                unsigned char sh = 0;
+                /* later starts: while ts_q <= te_r (they overlap iff te_q >= ts_r, which holds since ts_q >= ts_r) */
+                for (Py_ssize_t q = r + 1; q < k && rows[q].ts <= rows[r].te; ++q)
+                    if (rows[q].mx > rows[r].mx) { sh = 1; break; }
+                /* earlier or equal starts: overlap iff te_q >= ts_r; none can reach ts_r once ts_q < ts_r - dmax */
+                for (Py_ssize_t q = r - 1; !sh && q >= 0 && rows[q].ts >= rows[r].ts - dmax; --q)
+                    if (rows[q].te >= rows[r].ts && rows[q].mx > rows[r].mx) sh = 1;
+                out[rows[r].row] = sh;
+            }
+        }
+        res = PyLong_FromLong(0);
+    }
+done:
+    PyMem_Free(rows);
+    for (int i = 0; i < nb; ++i) PyBuffer_Release(&b[i]);
+    return res;
+}
+
 static PyMethodDef methods[] = {
+    {"shadow_units", shadow_units, METH_VARARGS, "shadow filter (analyze.py:282-328) per analyzer unit on column arrays"},
     {"build_signals", build_signals, METH_VARARGS, "column arrays of one engine call -> per-unit lists of Signal objects"},
     {NULL, NULL, 0, NULL},
 };

@@ -270,6 +270,33 @@ def test_shadow_sweep_equals_the_pairwise_definition_with_ties():
         assert np.array_equal(whole[m], pairwise(ts[m], du[m], mx[m]))
 
 
+def test_c_shadow_filter_per_unit_equals_the_pairwise_definition():
+    """csrc/rt_pyfinal.c shadow_units (what finalize_arrays runs): rows sorted by unit, every unit on its own, == the pairwise
+    definition of analyze.py:283-313 with ties, zero durations and touching intervals; a unit beyond its size limit is refused
+    (return 1, output untouched) so that the caller takes the numpy sweep."""
+    from pyradiotracking_b200 import _rtfinal
+
+    def pairwise(unit, ts, du, mx):
+        te = ts + du
+        return np.array([bool(((unit == unit[i]) & (ts[i] <= te) & (te[i] >= ts) & (mx > mx[i])).any()) for i in range(len(ts))], dtype=bool)
+
+    rng = np.random.default_rng(23)
+    for trial in range(200):
+        n = int(rng.integers(0, 300))
+        unit = np.sort(rng.integers(0, int(rng.integers(1, 9)), n)).astype(np.int64)
+        scale = int(rng.choice([1, 1000]))
+        ts = (rng.integers(0, 60, n) * scale).astype(np.int64)
+        du = (rng.integers(0, 25, n) * int(rng.choice([1, 700]))).astype(np.int64)
+        mx = np.round(rng.normal(-70, 3, n), int(rng.integers(0, 3)))
+        out = np.zeros(n, dtype=bool)
+        assert _rtfinal.shadow_units(unit, ts, du, mx, out.view(np.uint8)) == 0
+        assert np.array_equal(out, pairwise(unit, ts, du, mx)), trial
+    n = 8193
+    out = np.ones(n, dtype=bool)
+    z = np.zeros(n, dtype=np.int64)
+    assert _rtfinal.shadow_units(z, z, z, np.zeros(n), out.view(np.uint8)) == 1 and out.all()
+
+
 def test_unit_timestamps_and_parity_counters():
     """blocks_per_launch: unit u = stream * B + block starts `block` callback lengths after the launch (the reference's `_ts +=
     buffer_len_dt`, analyze.py:221); and oracle/check.py (the bench's parity gate) counts an identical result as identical."""
