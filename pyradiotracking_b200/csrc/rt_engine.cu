@@ -670,7 +670,7 @@ __global__ void untile_kernel(const float* S, float* out, int total, int n, floa
 // ---------------------------------------------------------------------------------------------
 #ifdef RT_LAB
 // tools/ only (tools/build_lab_lib.sh, never the shipped library): leave scan kernels out to time what each one costs the step
-extern "C" { int rt_lab_extract_mode = 0; int rt_lab_skip = 0; int rt_lab_lean_per_sm = 0; int rt_lab_extract_per_sm = 0; int rt_lab_s256 = 0; }      // skip: bit 0 row means, bit 1 probe, bit 2 extraction; lean CTAs per SM (0 = default)
+extern "C" { int rt_lab_extract_mode = 0; int rt_lab_skip = 0; int rt_lab_lean_per_sm = 0; int rt_lab_extract_per_sm = 0; int rt_lab_s256 = 0; int rt_lab_probe_ppt = 0; }      // skip: bit 0 row means, bit 1 probe, bit 2 extraction; lean CTAs per SM (0 = default)
 #define RT_LAB_SKIP(b) (rt_lab_skip & (b))
 #else
 #define RT_LAB_SKIP(b) 0
@@ -888,12 +888,14 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
         if (cfg->chunk_segs > 0) e->chunk_segs = cfg->chunk_segs;
     }
     {
-        // small launches (a single wideband stream): fewer probe columns per thread = more CTAs; 32 columns per thread would
-        // leave a 20 MS/s nperseg-1024 block with 16 probe CTAs, each a long chain of dependent round trips
+        // full-size probe kernel: as many CTAs as fit in ONE wave beside the resident spectrogram CTAs of the next launch (about one
+        // 256-thread CTA per SM).  Fewer probe columns per thread = more CTAs and shorter chains of round trips, but a second wave
+        // doubles the kernel: a 20 MS/s nperseg-4096 block took 46 us at 8 columns per thread (256 CTAs), 18 us at 16 (128 CTAs) and
+        // 57 us at 32 (64 CTAs); step 85.5 -> 67.2 us
         const long long bin_blocks = (n + 255) / 256;
-        for (int ppt = 32; ppt >= 8; ppt >>= 1) {
+        for (int ppt = 8; ppt <= 32; ppt <<= 1) {
             e->probe_ppt = ppt;
-            if (bin_blocks * ((e->n_probes + ppt - 1) / ppt) * e->n_units >= 2 * 148) break;
+            if (bin_blocks * ((e->n_probes + ppt - 1) / ppt) * e->n_units <= 148) break;
         }
     }
     e->n_chunks = (e->T + e->chunk_segs - 1) / e->chunk_segs;
@@ -1221,7 +1223,10 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     sc.widen = ((long long)e->n_units * e->T < 300000) ? 1 : 0;
     sc.work = e->d_work; sc.max_work = e->max_work; sc.counters = d_cnt; sc.rec = e->d_rec[slot]; sc.max_records = e->max_records;
     const int pbins = std::min(e->n, 256);
-    const int ppt = e->probe_ppt;
+    int ppt = e->probe_ppt;
+#ifdef RT_LAB
+    if (rt_lab_probe_ppt > 0) ppt = rt_lab_probe_ppt;
+#endif
     dim3 pgrid(((e->n + pbins - 1) / pbins) * ((e->n_probes + ppt - 1) / ppt), e->n_units);
 #define RT_PROBE(L)                                                                        \
     do {                                                                                   \
