@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--streams", type=int, default=64, help="streams per GPU")
     ap.add_argument("--profile", action="store_true", help="device-resident region only (for runs under ncu)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed batch")
+    ap.add_argument("--chunk-segs", type=int, default=-1, help="rt_config.chunk_segs (segments per spectrogram CTA); -1 = the workload's default")
     ap.add_argument("--fft-impl", default="auto", choices=["auto", "reg256", "tc256", "generic"],
                     help="spectrogram kernel: auto = reg256 (registers, packed fp32x2); tc256 = tensor-core stage 1 (tcgen05)")
     return ap.parse_args()
@@ -65,12 +66,16 @@ class Work:
 
         self.key = name
         self.streams = streams
+        self.chunk_segs = 0                                        # rt_config.chunk_segs: 0 = the engine's choice
         if name == "c2":
             self.w, self.bpl, self.n_blk = synth.C2, 1, 2
             self.label = "configs[1]: 64x2.4MS/s nperseg256 hamming -90dBW/5dB 8-40ms"
         else:
             self.w, self.bpl, self.n_blk = synth.C4, 10, 60
             self.label = "configs[3]: replay, 64 of 512 channels x 300kS/s per GPU, 60-block resident chunk, 10 blocks per launch"
+            # 640 analyzer units per launch: longer chunks than the engine's latency-minded default for 1171-segment blocks (64)
+            # amortise the CTA prologue; measured 0.3258 (64) / 0.3136 (128) / 0.3078 (192) / 0.3057 (256) / 0.3121 (384) ms per launch
+            self.chunk_segs = 256
         self.groups = self.n_blk // self.bpl                       # distinct launches before the chunk repeats
         self.samples_per_step = streams * self.bpl * self.w.block_samples
         self.bytes_per_step = 2 * self.samples_per_step
@@ -86,6 +91,7 @@ class Work:
 def analyzer_kwargs(wk, rank):
     w, n = wk.w, wk.streams
     return dict(
+        chunk_segs=wk.chunk_segs,
         devices=[str(rank * n + i) for i in range(n)], calibration_db=[0.0] * n,
         sample_rate=w.sample_rate, center_freq=w.center_freq, fft_nperseg=w.nperseg, fft_window="hamming",
         signal_min_duration_ms=w.signal_min_duration_ms, signal_max_duration_ms=w.signal_max_duration_ms,
@@ -350,6 +356,8 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     wk = Work(args.workload, args.streams)
+    if args.chunk_segs >= 0:
+        wk.chunk_segs = args.chunk_segs
     S = wk.streams
 
     # every rank keeps to its own share of the host cores: the generator pool, the CUDA driver threads, the finaliser
@@ -513,7 +521,7 @@ def run_b200(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": wk.config(l2=f"inputs larger than L2 ({wk.bytes_per_step / 1e6:.0f} MB per step, {G} alternating launches)",
-                                records_per_step=n_rec, extract_work_items_per_step=work_items, fft_impl=args.fft_impl,
+                                records_per_step=n_rec, extract_work_items_per_step=work_items, fft_impl=args.fft_impl, chunk_segs=wk.chunk_segs,
                                 host_cores_per_rank=n_cores, cpu_affinity=("all" if affinity is None else f"{affinity[0]}-{affinity[-1]}")),
             "ms_per_step_per_rank": {"min": min(ms_ranks) / args.steps, "median": statistics.median(ms_ranks) / args.steps,
                                      "max": max(ms_ranks) / args.steps, "all": [round(x / args.steps, 5) for x in ms_ranks]},
