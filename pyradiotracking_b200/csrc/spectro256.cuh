@@ -66,10 +66,14 @@ __device__ __forceinline__ void stg128_hint(float4* dst, float4 v, uint64_t pol)
 //   * inter-pass twiddles as (wr, wi) scalars: the lane swap / sign live in FFMA2 operand modifiers
 //   * invalid (ragged-tail) lanes masked by a 0/1 factor in the row-sum FMA instead of a branch
 // ---------------------------------------------------------------------------------------------
-template <int WARPS_, int MINB_>
+// LMAP: a segment's 16 threads are the lanes {0-3, 8-11, 16-19, 24-27} (+4 for the warp's second segment) instead of a half-warp, so
+// that with the time-pair S layout (TG = 2) each quarter-warp phase of a 128-bit store covers ONE 128-byte line (4 granules x 2 time
+// steps) instead of two half lines.  The shared-memory strides change with it: the two segments of a warp must sit 16 banks apart.
+template <int WARPS_, int MINB_, bool LMAP_ = false>
 struct R256v7T {
     static constexpr int WARPS = WARPS_, THREADS = 32 * WARPS_, STAGES = 4, MINB = MINB_;
-    static constexpr int RAW_STRIDE = 544, XROW = 36, XTILE = 16 * XROW;
+    static constexpr bool LMAP = LMAP_;
+    static constexpr int RAW_STRIDE = LMAP_ ? 576 : 544, XROW = 36, XTILE = 16 * XROW + (LMAP_ ? 16 : 0);
     static constexpr int STAGE_BYTES = 2 * RAW_STRIDE;                  // two segments per warp per round
     static constexpr int RAW_BYTES = WARPS * STAGES * STAGE_BYTES;
     static constexpr int XCH_BYTES = 2 * WARPS * XTILE * 4;
@@ -177,7 +181,10 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
     auto seg_rel = [](int it) { return TG > 2 ? (it / RPG) * GSEGS + 2 * (it % RPG) : it * C::SEGS_PER_ROUND; };
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     const int tid = threadIdx.x;
-    const int lane = tid & 31, h = lane >> 4, j = lane & 15;
+    const int lane = tid & 31;
+    const int h = C::LMAP ? (lane >> 2) & 1 : lane >> 4;                              // which of the warp's two segments
+    const int j = C::LMAP ? (lane & 3) | ((lane >> 3) << 2) : lane & 15;              // thread of the 16 x 16 FFT
+    const int hwi = 2 * (tid >> 5) + h;                                               // segment slot of the CTA
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler
     const int s = blockIdx.y;
     const int seg0 = blockIdx.x * a.chunk_segs;
@@ -194,7 +201,7 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
     const uint32_t sm0 = smem_u32(dyn_smem);
     const uint32_t wraw = sm0 + warp * (C::STAGES * C::STAGE_BYTES);
     const uint32_t wbar = sm0 + C::BAR_OFF + warp * (C::STAGES * 8);
-    const uint32_t xt = sm0 + C::RAW_BYTES + (tid >> 4) * (C::XTILE * 4);
+    const uint32_t xt = sm0 + C::RAW_BYTES + hwi * (C::XTILE * 4);
     const uint32_t my_u16 = wraw + h * C::RAW_STRIDE + 2 * j;        // + stage offset + 32*n1
     const uint32_t my_sum = wraw + h * C::RAW_STRIDE + 16 * j;       // + stage offset (+256)
     uint32_t xt_st = xt + 8 * j;                                      // + k1 * XROW * 4
@@ -396,7 +403,7 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
     // chunk row sums: fixed-order reduction over the half-warps, written in FFT bin order (fi = j + 16*k2)
     __syncthreads();
     float* red = reinterpret_cast<float*>(dyn_smem);
-    const int hw = tid >> 4;
+    const int hw = hwi;
 #pragma unroll
     for (int k2 = 0; k2 < 16; ++k2) red[hw * 256 + 16 * k2 + j] = PACC ? ((k2 & 1) ? c_im(acc2[k2 >> 1]) : c_re(acc2[k2 >> 1])) : acc[k2];
     __syncthreads();
@@ -411,9 +418,9 @@ __device__ __forceinline__ void spectro_reg256_v7_body(const SpectroArgs& a) {
 }
 
 // addresses pinned in registers (see PIN in spectro_reg256_v7_body)
-template <bool STORE, int TG = 1>
+template <bool STORE, int TG = 1, bool LMAP = false>
 __global__ void __launch_bounds__(R256v7::THREADS, 4) spectro_reg256_v7n(SpectroArgs a) {
-    spectro_reg256_v7_body<STORE, false, false, false, false, false, 0, true, false, R256v7, TG>(a);
+    spectro_reg256_v7_body<STORE, false, false, false, false, false, 0, true, false, R256v7T<4, 4, LMAP>, TG>(a);
 }
 
 }  // namespace rt

@@ -173,6 +173,8 @@ int main(int argc, char** argv) {
 #define RUNW(W, MB, CH) run_k(c, spectro_reg256_v7w<true, W, MB>, 32 * W, R256v7T<W, MB>::SMEM, "v7w W" #W " MB" #MB, CH)
     run_k(c, spectro_reg256_v7n<true>, R256v7::THREADS, R256v7::SMEM, "v7n", 192);
     run_k(c, spectro_reg256_v7n<true, 2>, R256v7::THREADS, R256v7::SMEM, "v7n TG2", 192);
+    run_k(c, spectro_reg256_v7n<true, 2, true>, R256v7::THREADS, R256v7T<4, 4, true>::SMEM, "v7n TG2 LMAP", 192);
+    run_k(c, spectro_reg256_v7n<true, 1, true>, R256v7::THREADS, R256v7T<4, 4, true>::SMEM, "v7n TG1 LMAP", 192);
     run_k(c, spectro_reg256_v7n<true, 4>, R256v7::THREADS, R256v7::SMEM, "v7n TG4", 192);
     run_k(c, spectro_reg256_v7n<true, 8>, R256v7::THREADS, R256v7::SMEM, "v7n TG8", 192);
     RUNW(4, 4, 192);
