@@ -463,6 +463,9 @@ __global__ void __launch_bounds__(128, 16) probe_lean_kernel(ScanArgs a) {
             bool keep = true;
             int lo = -1, hi = -1;
             bool lo_open = true, hi_open = true;
+#ifdef RT_LAB
+            if (a.lab_mode & 8) lo_open = hi_open = false;      // timing only: no neighbour loads (every hit survives)
+#endif
 #pragma unroll 1
             for (int d = 1; d <= PROBE_QUICK && (lo_open || hi_open); ++d) {
                 const int tl = ti - d, th = ti + d;
