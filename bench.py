@@ -415,7 +415,9 @@ def run_b200(args):
     for i in range(max(args.warmup, 1)):
         eng.launch(dev[i % G])
     n_rec = len(eng.fetch())
-    eng.enable_timing(4)
+    # per-kernel CUDA events (the roofline's kernel time) on every `period`-th launch: an event pair between two spectrogram kernels
+    # costs the step a few microseconds of launch gap, so a dozen samples per run are taken rather than one per launch
+    eng.enable_timing(max(4, args.steps // 12))
     eng.timing(reset=True)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
