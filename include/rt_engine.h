@@ -46,7 +46,7 @@ enum {
 
 /* scan_schedule: where the scan kernels (row mean, probe, extraction) of a launch run. */
 enum {
-    RT_SCAN_AUTO = 0,     /* RT_SCAN_LEAN for nperseg 256 launches of >= 300 k segments, otherwise RT_SCAN_OVERLAP */
+    RT_SCAN_AUTO = 0,     /* RT_SCAN_LEAN for nperseg 256 launches of >= 500 k segments, otherwise RT_SCAN_OVERLAP */
     RT_SCAN_SERIAL = 1,   /* on the launch stream, after the spectrogram (no overlap with the next launch) */
     RT_SCAN_OVERLAP = 2,  /* full-size scan kernels on an engine-internal high-priority stream */
     RT_SCAN_LEAN = 3      /* 32-register scan kernels that fit BESIDE the resident spectrogram CTAs of the next launch */

@@ -995,7 +995,9 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
     if (sched == RT_SCAN_AUTO)
         // lean only where it was measured to win: the register kernel (the tensor-core kernel owns its SMs) with at least
         // ~100 us of spectrogram per launch (short launches: the slower lean kernels become the critical path)
-        sched = (e->reg256 && !e->tc256 && (long long)e->n_units * e->T >= 300000) ? RT_SCAN_LEAN : RT_SCAN_OVERLAP;
+        // (round-2 kernels, 2.4 MS/s streams: 32 streams 112.5 overlap / 113.9 lean, 48: 151.3 / 153.3, 64: 197.4 / 189.0 us;
+        //  lean probe + full-size extraction: 188.0, full-size probe + lean extraction: 196.5)
+        sched = (e->reg256 && !e->tc256 && (long long)e->n_units * e->T >= 500000) ? RT_SCAN_LEAN : RT_SCAN_OVERLAP;
     if (sched != RT_SCAN_SERIAL) {
         // the scan kernels are small and latency bound: give them priority over the next launch's spectrogram CTAs
         int prio_lo = 0, prio_hi = 0;
