@@ -530,7 +530,7 @@ def run_b200(args):
             "clocks": clk,
             "e2e": e2e,
             "gpu_launches": int(tim["kernels"]),
-            "roofline": {"bound": "hbm", "kernel": "spectro_tc256" if args.fft_impl == "tc256" else "spectro_reg256_v7n", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "spectro_tc256" if args.fft_impl == "tc256" else "spectro_reg256_v8", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": recorded_traffic() if wk.key == "c2" else None, "peak_source": peak_kind,
                          "algorithmic_bytes_per_launch": wk.bytes_per_step, "kernel_ms": k_eff,
                          "kernel_ms_event_bracketed": k_ms,

@@ -82,6 +82,13 @@ constexpr int PERM_TG = RT_PERM_TG;
 // phase of its 128-bit stores then covers one whole 128-byte line; back to back 173.9 -> 169.7 us (one time step per row: 170.8 us)
 constexpr bool PERM_LMAP = PERM_TG == 2;
 using R256Prod = rt::R256v7T<4, 4, PERM_LMAP>;
+// the nperseg-256 register kernel of the product: v8 (spectro256.cuh) under the time-pair layout; lab builds with other
+// time groupings (tools/build_lab_lib.sh, RT_PERM_TG = 1 | 4 | 8) keep v7n, which knows all of them
+#if RT_PERM_TG == 2
+#define RT_SPECTRO_REG256 rt::spectro_reg256_v8<true, 2, 0>
+#else
+#define RT_SPECTRO_REG256 rt::spectro_reg256_v7n<true, PERM_TG, PERM_LMAP>
+#endif
 __host__ __device__ constexpr int perm256(int k) { return ((k >> 6) << 6) | ((k & 15) << 2) | ((k >> 4) & 3); }                // bin -> position
 __host__ __device__ constexpr int unperm256(int p) { return ((p >> 2) & 15) + 16 * (4 * (p >> 6) + (p & 3)); }                 // position -> bin
 // row position -> FFT bin for the layouts whose rows are not in bin order (n = bins per row)
@@ -1055,8 +1062,8 @@ int rt_engine_create(const rt_config* cfg, rt_engine** out) {
         const size_t smem = (size_t)n * (2 * sizeof(float2) + sizeof(float)) + 16;
         CUE(cudaFuncSetAttribute(spectro_generic<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     } else {
-        CUE((cudaFuncSetAttribute(rt::spectro_reg256_v7n<true, PERM_TG, PERM_LMAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, R256Prod::SMEM)));
-        CUE((cudaFuncSetAttribute(rt::spectro_reg256_v7n<true, PERM_TG, PERM_LMAP>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)));
+        CUE((cudaFuncSetAttribute(RT_SPECTRO_REG256, cudaFuncAttributeMaxDynamicSharedMemorySize, R256Prod::SMEM)));
+        CUE((cudaFuncSetAttribute(RT_SPECTRO_REG256, cudaFuncAttributePreferredSharedMemoryCarveout, 100)));
     }
 #undef CUE
     *out = e;
@@ -1177,7 +1184,7 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
         ta.store = 1; ta.dbg = 0; ta.prof = nullptr;
         rt::spectro_tc256_k<2><<<e->tc_grid, 512, rt::Tc256<2>::SMEM, st>>>(ta);
     } else if (use_reg) {
-        rt::spectro_reg256_v7n<true, PERM_TG, PERM_LMAP><<<grid, R256Prod::THREADS, R256Prod::SMEM, st>>>(sa);
+        RT_SPECTRO_REG256<<<grid, R256Prod::THREADS, R256Prod::SMEM, st>>>(sa);
 #ifdef RT_LAB
     } else if (e->s256 && aligned) {
         if (e->n == 4096) rt::spectro_s256_k<4096><<<grid, 256, rt::S256Cfg<4096>::SMEM, st>>>(sa);

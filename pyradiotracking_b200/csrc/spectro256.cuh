@@ -423,4 +423,196 @@ __global__ void __launch_bounds__(R256v7::THREADS, 4) spectro_reg256_v7n(Spectro
     spectro_reg256_v7_body<STORE, false, false, false, false, false, 0, true, false, R256v7T<4, 4, LMAP>, TG>(a);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// v8 (round 2, session 3): the data flow of v7n (LMAP lane mapping, TG = 1 | 2 time grouping of S, pinned addresses, running TMA
+// source pointer) with a cheaper front end:
+//   * bytes -> fp16 pair with ONE PRMT per complex sample (0x6400 | b = 1024 + b in fp16, I in the low half, Q in the high half);
+//     the mixed-precision add of sm_100 (PTX add.rn.f32.f16, SASS FHADD) widens to fp32 and subtracts 1024 + mean in one instruction
+//     per component -- bit for bit the value v7n's PRMT x 2 + FADD2 produced (b - sum / 256 is exact in fp32);
+//   * the segment's byte sums come from those 16 packed words the thread already holds: eight 3-input integer adds give
+//     sum(I) + 65536 sum(Q) of the thread's samples, one REDUX per segment of the warp adds the 16 threads -- instead of a second pass
+//     over the raw bytes (2 LDS.128 + 16 dp4a, which are FMA-pipe instructions, + 2 REDUX and the field shifts);
+//   * XV bit 0: the loads, the conversion to fp16 pairs and the sums of round it + 1 are issued at the end of round it (their latency chain
+//     LDS -> PRMT -> IADD3 -> REDUX overlaps the stores and the loop bookkeeping instead of standing in front of the butterflies);
+//     bit 1: the PRMT constant lives in a register (ptxas otherwise copies the selector into five registers per round);
+//     bit 2: row sums as 8 packed FMAs.
+// ---------------------------------------------------------------------------------------------
+template <bool STORE, int TG, int XV, class C = R256v7T<4, 4, true>>
+__device__ __forceinline__ void spectro_reg256_v8_body(const SpectroArgs& a) {
+    static_assert(TG == 1 || TG == 2, "time group");
+    static_assert(C::LMAP, "v8 uses the LMAP lane mapping");
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int h = (lane >> 2) & 1;                                    // which of the warp's two segments
+    const int j = (lane & 3) | ((lane >> 3) << 2);                    // thread of the 16 x 16 FFT
+    const int hwi = 2 * (tid >> 5) + h;                               // segment slot of the CTA
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler
+    const int s = blockIdx.y;
+    const int seg0 = blockIdx.x * a.chunk_segs;
+    const int seg1 = min(a.T, seg0 + a.chunk_segs);
+    const int first = seg0 + 2 * warp;
+    const int n_it = (seg1 - first + C::SEGS_PER_ROUND - 1) / C::SEGS_PER_ROUND;   // warp-uniform
+
+    const uint32_t sm0 = smem_u32(dyn_smem);
+    const uint32_t wraw = sm0 + warp * (C::STAGES * C::STAGE_BYTES);
+    const uint32_t wbar = sm0 + C::BAR_OFF + warp * (C::STAGES * 8);
+    const uint32_t xt = sm0 + C::RAW_BYTES + hwi * (C::XTILE * 4);
+    uint32_t my_u16 = wraw + h * C::RAW_STRIDE + 2 * j;               // + stage offset + 32 * n1
+    uint32_t xt_st = xt + 8 * j;                                      // + k1 * XROW * 4
+    uint32_t xt_ld = xt + j * (C::XROW * 4);                          // + 16 * c
+    unsigned k64 = 0x64646464u;
+    int hsel = h;
+    asm volatile("" : "+r"(my_u16), "+r"(xt_st), "+r"(xt_ld), "+r"(hsel));   // opaque: ptxas otherwise re-derives them from SR_TID.X every round
+    if (XV & 2) asm volatile("" : "+r"(k64));
+    const uint8_t* gsrc = a.unit_base(s) + (size_t)first * 512;     // segment pair of round it: + it * SEGS_PER_ROUND * 512
+    const int last_seg = seg1 - 1;
+
+    if (elect_one()) {
+#pragma unroll
+        for (int st = 0; st < C::STAGES; ++st)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(wbar + 8 * st) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int st = 0; st < C::STAGES; ++st)
+            if (st < n_it) {
+                const uint8_t* p0 = gsrc + (size_t)st * (C::SEGS_PER_ROUND * 512);
+                const uint8_t* p1 = (first + st * C::SEGS_PER_ROUND + 1 <= last_seg) ? p0 + 512 : p0;   // ragged tail: the same segment twice
+                const uint32_t bar = wbar + 8 * st, dst = wraw + st * C::STAGE_BYTES;
+                mbar_expect_tx_a(bar, 1024);
+                bulk_g2s_a(dst, p0, 512, bar);
+                bulk_g2s_a(dst + C::RAW_STRIDE, p1, 512, bar);
+            }
+    }
+
+    // per-thread constants: window at samples 16 * n1 + j, inter-pass twiddles W256^{j * k1}
+    float wj[16], twr[16], twi[16], acc[16];
+    cpk acc2[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc2[c] = c_make(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        wj[i] = a.win[16 * i + j];
+        const float2 t = a.tw[(j * i) & 255];
+        twr[i] = t.x;
+        twi[i] = t.y;
+        acc[i] = 0.f;
+    }
+    __syncwarp();                                   // barriers initialised before anyone polls them
+
+    unsigned hv[16];                                // (1024 + I) | (1024 + Q) << 16 as an fp16 pair, samples 16 * n1 + j
+    cpk nc = c_make(0.f, 0.f);                      // -(1024 + mean_I), -(1024 + mean_Q)
+    auto load_round = [&](uint32_t off) {
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) hv[n1] = __byte_perm(lds_u16(my_u16 + off + 32 * n1), k64, 0x5140);
+        unsigned t = 0;
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) t += hv[n1];
+        t -= 0x40064000u;                           // 16 x 0x64006400 mod 2^32: t = sum I + 65536 sum Q over this thread's 16 samples
+        const unsigned r0 = __reduce_add_sync(0xffffffffu, hsel ? 0u : t), r1 = __reduce_add_sync(0xffffffffu, hsel ? t : 0u);
+        const unsigned tot = hsel ? r1 : r0;        // the segment's byte sums (each < 2^16)
+        // (2^23 + sum) * -2^-8 + 31744 = -(1024 + sum / 256), exact
+        nc = c_fma_s(c_make(__uint_as_float(0x4B000000u | (tot & 0xffffu)), __uint_as_float(0x4B000000u | (tot >> 16))), -0.00390625f, c_make(31744.f, 31744.f));
+    };
+
+    if (n_it > 0) {
+        mbar_wait(wbar, 0);
+        if (XV & 1) load_round(0);
+    }
+    // TG = 1: row (first + h), floats 4 j ...; TG = 2: row pair first / 2 (first is even), granule j of 8 floats, half h of it
+    float* sdst = a.S + (size_t)s * a.S_stream_stride + (TG == 2 ? (size_t)first * 256 + 8 * j + 4 * h : (size_t)(first + h) * 256 + 4 * j);   // += 8 * 256 floats per round
+    uint32_t st_off = 0, st_bar = wbar;
+    unsigned phase = 0;
+    const uint8_t* g_next = gsrc + (size_t)C::STAGES * (C::SEGS_PER_ROUND * 512);   // source of the next round to be issued
+    int sg_next = first + C::STAGES * C::SEGS_PER_ROUND;
+    int seg = first + h;
+
+    for (int it = 0; it < n_it; ++it) {
+        if (!(XV & 1)) load_round(st_off);
+        cpk v[16];
+        {
+            const float ncI = c_re(nc), ncQ = c_im(nc);
+#pragma unroll
+            for (int n1 = 0; n1 < 16; ++n1) {
+                float re, im;
+                asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(re) : "h"((unsigned short)(hv[n1] & 0xffffu)), "f"(ncI));
+                asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(im) : "h"((unsigned short)(hv[n1] >> 16)), "f"(ncQ));
+                v[n1] = c_make(re, im);
+            }
+        }
+        // this stage's bytes are in registers: refill it with the segments STAGES rounds ahead
+        __syncwarp();
+        if (it + C::STAGES < n_it) {
+            if (elect_one()) {
+                const uint8_t* p1 = (sg_next + 1 <= last_seg) ? g_next + 512 : g_next;
+                mbar_expect_tx_a(st_bar, 1024);
+                bulk_g2s_a(wraw + st_off, g_next, 512, st_bar);
+                bulk_g2s_a(wraw + st_off + C::RAW_STRIDE, p1, 512, st_bar);
+            }
+        }
+        g_next += C::SEGS_PER_ROUND * 512;
+        sg_next += C::SEGS_PER_ROUND;
+        st_off += C::STAGE_BYTES; st_bar += 8;
+        if (st_off == C::STAGES * C::STAGE_BYTES) { st_off = 0; st_bar = wbar; phase ^= 1; }
+        if (!(XV & 1) && it + 1 < n_it) mbar_wait(st_bar, phase);
+
+        cdft16_win(v, wj);                          // over n1 -> k1, for column n2 = j
+        // inter-pass twiddles, then the 16 x 16 transpose through shared memory
+        sts_64(xt_st, v[0].v);
+#pragma unroll
+        for (int k1 = 1; k1 < 16; ++k1) sts_64(xt_st + k1 * (C::XROW * 4), c_mul(v[k1], twr[k1], twi[k1]).v);
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) lds_2x64(xt_ld + 16 * c, v[2 * c].v, v[2 * c + 1].v);
+        // (the tile is rewritten only after the next round's __syncwarp)
+        cdft16(v);                                  // over n2 -> k2, for k1 = j: bin = j + 16 * k2
+        const bool valid = seg <= last_seg;
+        const float m = valid ? 1.f : 0.f;
+        float p[16];
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) {
+            const float re = c_re(v[k2]), im = c_im(v[k2]);
+            p[k2] = fmaf(im, im, re * re);
+            if (!(XV & 4)) acc[k2] = fmaf(p[k2], m, acc[k2]);
+        }
+        if (XV & 4) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc2[c] = c_fma_s(c_make(p[2 * c], p[2 * c + 1]), m, acc2[c]);
+        }
+        if ((XV & 1) && it + 1 < n_it) {            // next round's samples and sums: the chain LDS -> PRMT -> IADD3 -> REDUX runs under the stores
+            mbar_wait(st_bar, phase);
+            load_round(st_off);
+        }
+        if (STORE) {
+            if (valid) {
+                float4* dst = reinterpret_cast<float4*>(sdst);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) dst[16 * TG * c] = make_float4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);   // 64 positions further
+            }
+            sdst += C::SEGS_PER_ROUND * 256;
+        }
+        seg += C::SEGS_PER_ROUND;
+    }
+
+    // chunk row sums: fixed-order reduction over the CTA's segment slots, written in the order of the S rows (PERM position)
+    __syncthreads();
+    float* red = reinterpret_cast<float*>(dyn_smem);
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) red[hwi * 256 + 16 * k2 + j] = (XV & 4) ? ((k2 & 1) ? c_im(acc2[k2 >> 1]) : c_re(acc2[k2 >> 1])) : acc[k2];
+    __syncthreads();
+    float* pd = a.part + ((size_t)s * a.n_chunks + blockIdx.x) * 256;
+    for (int fi = tid; fi < 256; fi += C::THREADS) {
+        float t = 0.f;
+#pragma unroll
+        for (int hh = 0; hh < 2 * C::WARPS; ++hh) t += red[hh * 256 + fi];
+        pd[((fi >> 6) << 6) | ((fi & 15) << 2) | ((fi >> 4) & 3)] = t;
+    }
+}
+
+template <bool STORE, int TG = 2, int XV = 0>
+__global__ void __launch_bounds__(R256v7::THREADS, 4) spectro_reg256_v8(SpectroArgs a) {
+    spectro_reg256_v8_body<STORE, TG, XV>(a);
+}
+
 }  // namespace rt
