@@ -507,8 +507,16 @@ __device__ __forceinline__ void spectro_reg256_v8_body(const SpectroArgs& a) {
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) hv[n1] = __byte_perm(lds_u16(my_u16 + off + 32 * n1), k64, 0x5140);
         unsigned t = 0;
+        if (XV & 8) {                               // three levels of 3-input adds instead of a chain of eight
+            const unsigned s0 = hv[0] + hv[1] + hv[2], s1 = hv[3] + hv[4] + hv[5], s2 = hv[6] + hv[7] + hv[8];
+            const unsigned s3 = hv[9] + hv[10] + hv[11], s4 = hv[12] + hv[13] + hv[14];
+            unsigned u0 = s0 + s1 + s2, u1 = s3 + s4 + hv[15];
+            asm volatile("" : "+r"(u0), "+r"(u1));  // keep the tree (ptxas re-associates into a chain otherwise)
+            t = u0 + u1;
+        } else {
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) t += hv[n1];
+            for (int n1 = 0; n1 < 16; ++n1) t += hv[n1];
+        }
         t -= 0x40064000u;                           // 16 x 0x64006400 mod 2^32: t = sum I + 65536 sum Q over this thread's 16 samples
         const unsigned r0 = __reduce_add_sync(0xffffffffu, hsel ? 0u : t), r1 = __reduce_add_sync(0xffffffffu, hsel ? t : 0u);
         const unsigned tot = hsel ? r1 : r0;        // the segment's byte sums (each < 2^16)
@@ -518,7 +526,7 @@ __device__ __forceinline__ void spectro_reg256_v8_body(const SpectroArgs& a) {
 
     if (n_it > 0) {
         mbar_wait(wbar, 0);
-        if (XV & 1) load_round(0);
+        if (XV & 17) load_round(0);
     }
     // TG = 1: row (first + h), floats 4 j ...; TG = 2: row pair first / 2 (first is even), granule j of 8 floats, half h of it
     float* sdst = a.S + (size_t)s * a.S_stream_stride + (TG == 2 ? (size_t)first * 256 + 8 * j + 4 * h : (size_t)(first + h) * 256 + 4 * j);   // += 8 * 256 floats per round
@@ -529,7 +537,7 @@ __device__ __forceinline__ void spectro_reg256_v8_body(const SpectroArgs& a) {
     int seg = first + h;
 
     for (int it = 0; it < n_it; ++it) {
-        if (!(XV & 1)) load_round(st_off);
+        if (!(XV & 17)) load_round(st_off);
         cpk v[16];
         {
             const float ncI = c_re(nc), ncQ = c_im(nc);
@@ -555,7 +563,7 @@ __device__ __forceinline__ void spectro_reg256_v8_body(const SpectroArgs& a) {
         sg_next += C::SEGS_PER_ROUND;
         st_off += C::STAGE_BYTES; st_bar += 8;
         if (st_off == C::STAGES * C::STAGE_BYTES) { st_off = 0; st_bar = wbar; phase ^= 1; }
-        if (!(XV & 1) && it + 1 < n_it) mbar_wait(st_bar, phase);
+        if (!(XV & 17) && it + 1 < n_it) mbar_wait(st_bar, phase);
 
         cdft16_win(v, wj);                          // over n1 -> k1, for column n2 = j
         // inter-pass twiddles, then the 16 x 16 transpose through shared memory
@@ -591,6 +599,10 @@ __device__ __forceinline__ void spectro_reg256_v8_body(const SpectroArgs& a) {
                 for (int c = 0; c < 4; ++c) dst[16 * TG * c] = make_float4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);   // 64 positions further
             }
             sdst += C::SEGS_PER_ROUND * 256;
+        }
+        if ((XV & 16) && it + 1 < n_it) {           // the same, behind the stores (p is dead: fewer live registers)
+            mbar_wait(st_bar, phase);
+            load_round(st_off);
         }
         seg += C::SEGS_PER_ROUND;
     }

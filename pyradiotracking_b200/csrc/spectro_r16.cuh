@@ -20,7 +20,7 @@
 //     exchange indices are affine in the unrolled loop index), held as 32-bit shared addresses;
 //   * the pass twiddles live in per-pass tables laid out [i][thread] (pass 1) and [i][thread / 16] (pass 2): consecutive
 //     lanes read consecutive 8-byte entries (no bank conflicts) instead of gathering W_N^{b i} out of one table of N entries;
-//   * the window is folded into the first butterfly layer (cdft16_win), the byte -> float conversion is two packed adds;
+//   * the window is folded into the first butterfly layer (cdft16_win); byte -> float: one PRMT per sample (fp16 pair) + two FHADD;
 //   * the segment's byte sums go through per-warp slots (double-buffered) instead of shared-memory atomics: one team
 //     barrier less per segment and no reset.
 #pragma once
@@ -142,13 +142,16 @@ __global__ void __maxnreg__(R16Cfg<N>::MAXR) spectro_r16_k(SpectroArgs a) {
         const uint32_t sb = sumb + (it & 1) * (C::TW * 8);
 
         // ---- gather the 16 first-pass inputs, byte sums for the detrend (exact integers)
+        // (like spectro_reg256_v8) one PRMT per sample builds the fp16 pair (1024 + I) | (1024 + Q) << 16; the integer sum of the 16
+        // packed words minus 16 x 0x64006400 is sum I + 65536 sum Q of this thread's samples
         unsigned u[16];
         unsigned packed = 0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            u[i] = lds_u16(rb + i * (2 * M1));
-            packed += __byte_perm(u[i], 0, 0x4140);            // I in the low half, Q in the high half (each <= 16 * 255)
+            u[i] = __byte_perm(lds_u16(rb + i * (2 * M1)), 0x64646464u, 0x5140);
+            packed += u[i];
         }
+        packed -= 0x40064000u;                                 // I in the low half, Q in the high half (each <= 16 * 255)
         const unsigned sI = __reduce_add_sync(0xffffffffu, packed & 0xffffu);
         const unsigned sQ = __reduce_add_sync(0xffffffffu, packed >> 16);
         if (lane == 0) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(sb + 8 * wt), "r"(sI), "r"(sQ) : "memory");
@@ -160,15 +163,16 @@ __global__ void __maxnreg__(R16Cfg<N>::MAXR) spectro_r16_k(SpectroArgs a) {
             tI += q.x + q.z;
             tQ += q.y + q.w;
         }
-        // mean = sum / N is exact in fp32 (sum < 2^24, N a power of two) and so is (float)byte - mean
-        const cpk mean = c_make((float)tI * (1.f / N), (float)tQ * (1.f / N));
-        const cpk magic = c_make(8388608.f, 8388608.f);
+        // mean = sum / N is exact in fp32 (sum < 2^24, N a power of two), so are -(1024 + mean) and (1024 + byte) - (1024 + mean);
+        // add.rn.f32.f16 (SASS FHADD) widens the fp16 half and subtracts in one instruction
+        const float ncI = fmaf((float)tI, -1.f / N, -1024.f), ncQ = fmaf((float)tQ, -1.f / N, -1024.f);
         cpk v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            // 0x4B0000bb = 2^23 + byte (no I2F); minus 2^23 and minus the mean are both exact
-            const cpk f = c_make(__uint_as_float(__byte_perm(u[i], 0x4B000000u, 0x7540)), __uint_as_float(__byte_perm(u[i], 0x4B000000u, 0x7541)));
-            v[i] = c_sub(c_sub(f, magic), mean);
+            float re, im;
+            asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(re) : "h"((unsigned short)(u[i] & 0xffffu)), "f"(ncI));
+            asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(im) : "h"((unsigned short)(u[i] >> 16)), "f"(ncQ));
+            v[i] = c_make(re, im);
         }
 
         // ---- pass 1: ncur = N, stride 1: p = b, q = 0; y[16 b + i] = W_N^{b i} DFT16(w x)[i]
