@@ -85,7 +85,7 @@ using R256Prod = rt::R256v7T<4, 4, PERM_LMAP>;
 // the nperseg-256 register kernel of the product: v8 (spectro256.cuh) under the time-pair layout; lab builds with other
 // time groupings (tools/build_lab_lib.sh, RT_PERM_TG = 1 | 4 | 8) keep v7n, which knows all of them
 #if RT_PERM_TG == 2
-#define RT_SPECTRO_REG256 rt::spectro_reg256_v8<true, 2, 0>
+#define RT_SPECTRO_REG256 rt::spectro_reg256_v8<true, 2>
 #else
 #define RT_SPECTRO_REG256 rt::spectro_reg256_v7n<true, PERM_TG, PERM_LMAP>
 #endif

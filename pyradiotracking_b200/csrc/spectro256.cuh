@@ -5,9 +5,9 @@
 //
 // 16 threads (a half-warp) hold one 256-point FFT as a 16x16 Cooley-Tukey in registers; every complex
 // value is one packed register pair (fft_cpk.cuh).  A warp works on 2*NSEG consecutive segments per
-// round, fed by a per-warp ring of TMA bulk copies.  The kernel body is a template so that the engine (which
-// instantiates only spectro_reg256_v7n) and tools/spectro_lab.cu (variant timing on the GPU box; the losing variants
-// live in tools/spectro256_lab.cuh) compile the very same source.
+// round, fed by a per-warp ring of TMA bulk copies.  The engine instantiates spectro_reg256_v8 (end of this file: v7n with a
+// cheaper byte -> float front end); spectro_reg256_v7n and its template switches stay for tools/spectro_lab.cu (variant timing on
+// the GPU box; the other losing variants live in tools/spectro256_lab.cuh) and for lab builds of the engine with other S layouts.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -425,20 +425,22 @@ __global__ void __launch_bounds__(R256v7::THREADS, 4) spectro_reg256_v7n(Spectro
 
 
 // ---------------------------------------------------------------------------------------------
-// v8 (round 2, session 3): the data flow of v7n (LMAP lane mapping, TG = 1 | 2 time grouping of S, pinned addresses, running TMA
-// source pointer) with a cheaper front end:
+// v8 (round 2, session 3) -- the engine's nperseg-256 kernel.  The data flow of v7n (LMAP lane mapping, TG = 1 | 2 time grouping of
+// S, pinned addresses, running TMA source pointer) with a cheaper front end:
 //   * bytes -> fp16 pair with ONE PRMT per complex sample (0x6400 | b = 1024 + b in fp16, I in the low half, Q in the high half);
-//     the mixed-precision add of sm_100 (PTX add.rn.f32.f16, SASS FHADD) widens to fp32 and subtracts 1024 + mean in one instruction
-//     per component -- bit for bit the value v7n's PRMT x 2 + FADD2 produced (b - sum / 256 is exact in fp32);
+//     the mixed-precision add of sm_100 (PTX add.rn.f32.f16, SASS FHADD: one FMA-pipe cycle, tools/ubench_mix3.cu) widens to fp32
+//     and subtracts 1024 + mean in one instruction per component -- bit for bit the value v7n's PRMT x 2 + FADD2 produced
+//     (b - sum / 256 is exact in fp32);
 //   * the segment's byte sums come from those 16 packed words the thread already holds: eight 3-input integer adds give
 //     sum(I) + 65536 sum(Q) of the thread's samples, one REDUX per segment of the warp adds the 16 threads -- instead of a second pass
-//     over the raw bytes (2 LDS.128 + 16 dp4a, which are FMA-pipe instructions, + 2 REDUX and the field shifts);
-//   * XV bit 0: the loads, the conversion to fp16 pairs and the sums of round it + 1 are issued at the end of round it (their latency chain
-//     LDS -> PRMT -> IADD3 -> REDUX overlaps the stores and the loop bookkeeping instead of standing in front of the butterflies);
-//     bit 1: the PRMT constant lives in a register (ptxas otherwise copies the selector into five registers per round);
-//     bit 2: row sums as 8 packed FMAs.
+//     over the raw bytes (2 LDS.128 + 16 dp4a, which are two FMA-pipe cycles each, + 2 REDUX and the field shifts).
+// S and the row sums are bit-identical to v7n's; 112 registers; back to back 170 -> 161 us at configs[1] (153 us without the S stores).
+// Measured and dropped (profiles/r02_v8_lab.txt): loads / sums of round it + 1 issued at the end of round it (128 registers, 165 us),
+// a tree instead of a chain of integer adds, the PRMT constant pinned in a register, packed row-sum FMAs, L2 eviction hints on the
+// TMA loads and / or the S stores -- all within +-0.5 us; integer detrend + I2F (a non-FMA pipe) instead of FHADD: 32 FMA-pipe cycles
+// less but 56 instructions more per round, 168 us -- issue slots and the FMA pipe bind together.
 // ---------------------------------------------------------------------------------------------
-template <bool STORE, int TG, int XV, class C = R256v7T<4, 4, true>>
+template <bool STORE, int TG, class C = R256v7T<4, 4, true>>
 __device__ __forceinline__ void spectro_reg256_v8_body(const SpectroArgs& a) {
     static_assert(TG == 1 || TG == 2, "time group");
     static_assert(C::LMAP, "v8 uses the LMAP lane mapping");
@@ -462,10 +464,8 @@ __device__ __forceinline__ void spectro_reg256_v8_body(const SpectroArgs& a) {
     uint32_t my_u16 = wraw + h * C::RAW_STRIDE + 2 * j;               // + stage offset + 32 * n1
     uint32_t xt_st = xt + 8 * j;                                      // + k1 * XROW * 4
     uint32_t xt_ld = xt + j * (C::XROW * 4);                          // + 16 * c
-    unsigned k64 = 0x64646464u;
     int hsel = h;
     asm volatile("" : "+r"(my_u16), "+r"(xt_st), "+r"(xt_ld), "+r"(hsel));   // opaque: ptxas otherwise re-derives them from SR_TID.X every round
-    if (XV & 2) asm volatile("" : "+r"(k64));
     const uint8_t* gsrc = a.unit_base(s) + (size_t)first * 512;     // segment pair of round it: + it * SEGS_PER_ROUND * 512
     const int last_seg = seg1 - 1;
 
@@ -488,9 +488,6 @@ __device__ __forceinline__ void spectro_reg256_v8_body(const SpectroArgs& a) {
 
     // per-thread constants: window at samples 16 * n1 + j, inter-pass twiddles W256^{j * k1}
     float wj[16], twr[16], twi[16], acc[16];
-    cpk acc2[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) acc2[c] = c_make(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         wj[i] = a.win[16 * i + j];
@@ -501,33 +498,7 @@ __device__ __forceinline__ void spectro_reg256_v8_body(const SpectroArgs& a) {
     }
     __syncwarp();                                   // barriers initialised before anyone polls them
 
-    unsigned hv[16];                                // (1024 + I) | (1024 + Q) << 16 as an fp16 pair, samples 16 * n1 + j
-    cpk nc = c_make(0.f, 0.f);                      // -(1024 + mean_I), -(1024 + mean_Q)
-    auto load_round = [&](uint32_t off) {
-#pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) hv[n1] = __byte_perm(lds_u16(my_u16 + off + 32 * n1), k64, 0x5140);
-        unsigned t = 0;
-        if (XV & 8) {                               // three levels of 3-input adds instead of a chain of eight
-            const unsigned s0 = hv[0] + hv[1] + hv[2], s1 = hv[3] + hv[4] + hv[5], s2 = hv[6] + hv[7] + hv[8];
-            const unsigned s3 = hv[9] + hv[10] + hv[11], s4 = hv[12] + hv[13] + hv[14];
-            unsigned u0 = s0 + s1 + s2, u1 = s3 + s4 + hv[15];
-            asm volatile("" : "+r"(u0), "+r"(u1));  // keep the tree (ptxas re-associates into a chain otherwise)
-            t = u0 + u1;
-        } else {
-#pragma unroll
-            for (int n1 = 0; n1 < 16; ++n1) t += hv[n1];
-        }
-        t -= 0x40064000u;                           // 16 x 0x64006400 mod 2^32: t = sum I + 65536 sum Q over this thread's 16 samples
-        const unsigned r0 = __reduce_add_sync(0xffffffffu, hsel ? 0u : t), r1 = __reduce_add_sync(0xffffffffu, hsel ? t : 0u);
-        const unsigned tot = hsel ? r1 : r0;        // the segment's byte sums (each < 2^16)
-        // (2^23 + sum) * -2^-8 + 31744 = -(1024 + sum / 256), exact
-        nc = c_fma_s(c_make(__uint_as_float(0x4B000000u | (tot & 0xffffu)), __uint_as_float(0x4B000000u | (tot >> 16))), -0.00390625f, c_make(31744.f, 31744.f));
-    };
-
-    if (n_it > 0) {
-        mbar_wait(wbar, 0);
-        if (XV & 17) load_round(0);
-    }
+    if (n_it > 0) mbar_wait(wbar, 0);
     // TG = 1: row (first + h), floats 4 j ...; TG = 2: row pair first / 2 (first is even), granule j of 8 floats, half h of it
     float* sdst = a.S + (size_t)s * a.S_stream_stride + (TG == 2 ? (size_t)first * 256 + 8 * j + 4 * h : (size_t)(first + h) * 256 + 4 * j);   // += 8 * 256 floats per round
     uint32_t st_off = 0, st_bar = wbar;
@@ -537,17 +508,26 @@ __device__ __forceinline__ void spectro_reg256_v8_body(const SpectroArgs& a) {
     int seg = first + h;
 
     for (int it = 0; it < n_it; ++it) {
-        if (!(XV & 17)) load_round(st_off);
-        cpk v[16];
-        {
-            const float ncI = c_re(nc), ncQ = c_im(nc);
+        // this thread's 16 samples as fp16 pairs (1024 + I) | (1024 + Q) << 16, and the segment's byte sums from the same words
+        unsigned hv[16];
 #pragma unroll
-            for (int n1 = 0; n1 < 16; ++n1) {
-                float re, im;
-                asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(re) : "h"((unsigned short)(hv[n1] & 0xffffu)), "f"(ncI));
-                asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(im) : "h"((unsigned short)(hv[n1] >> 16)), "f"(ncQ));
-                v[n1] = c_make(re, im);
-            }
+        for (int n1 = 0; n1 < 16; ++n1) hv[n1] = __byte_perm(lds_u16(my_u16 + st_off + 32 * n1), 0x64646464u, 0x5140);
+        unsigned t = 0;
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) t += hv[n1];
+        t -= 0x40064000u;                           // 16 x 0x64006400 mod 2^32: t = sum I + 65536 sum Q over this thread's 16 samples
+        const unsigned r0 = __reduce_add_sync(0xffffffffu, hsel ? 0u : t), r1 = __reduce_add_sync(0xffffffffu, hsel ? t : 0u);
+        const unsigned tot = hsel ? r1 : r0;        // the segment's byte sums (each < 2^16)
+        // (2^23 + sum) * -2^-8 + 31744 = -(1024 + sum / 256), exact: scipy's detrend='constant' on the raw bytes
+        const cpk nc = c_fma_s(c_make(__uint_as_float(0x4B000000u | (tot & 0xffffu)), __uint_as_float(0x4B000000u | (tot >> 16))), -0.00390625f, c_make(31744.f, 31744.f));
+        const float ncI = c_re(nc), ncQ = c_im(nc);
+        cpk v[16];
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) {
+            float re, im;
+            asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(re) : "h"((unsigned short)(hv[n1] & 0xffffu)), "f"(ncI));
+            asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(im) : "h"((unsigned short)(hv[n1] >> 16)), "f"(ncQ));
+            v[n1] = c_make(re, im);
         }
         // this stage's bytes are in registers: refill it with the segments STAGES rounds ahead
         __syncwarp();
@@ -563,7 +543,7 @@ __device__ __forceinline__ void spectro_reg256_v8_body(const SpectroArgs& a) {
         sg_next += C::SEGS_PER_ROUND;
         st_off += C::STAGE_BYTES; st_bar += 8;
         if (st_off == C::STAGES * C::STAGE_BYTES) { st_off = 0; st_bar = wbar; phase ^= 1; }
-        if (!(XV & 17) && it + 1 < n_it) mbar_wait(st_bar, phase);
+        if (it + 1 < n_it) mbar_wait(st_bar, phase);                 // (rarely blocks: the copy was issued three rounds ago)
 
         cdft16_win(v, wj);                          // over n1 -> k1, for column n2 = j
         // inter-pass twiddles, then the 16 x 16 transpose through shared memory
@@ -582,15 +562,7 @@ __device__ __forceinline__ void spectro_reg256_v8_body(const SpectroArgs& a) {
         for (int k2 = 0; k2 < 16; ++k2) {
             const float re = c_re(v[k2]), im = c_im(v[k2]);
             p[k2] = fmaf(im, im, re * re);
-            if (!(XV & 4)) acc[k2] = fmaf(p[k2], m, acc[k2]);
-        }
-        if (XV & 4) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) acc2[c] = c_fma_s(c_make(p[2 * c], p[2 * c + 1]), m, acc2[c]);
-        }
-        if ((XV & 1) && it + 1 < n_it) {            // next round's samples and sums: the chain LDS -> PRMT -> IADD3 -> REDUX runs under the stores
-            mbar_wait(st_bar, phase);
-            load_round(st_off);
+            acc[k2] = fmaf(p[k2], m, acc[k2]);
         }
         if (STORE) {
             if (valid) {
@@ -600,10 +572,6 @@ __device__ __forceinline__ void spectro_reg256_v8_body(const SpectroArgs& a) {
             }
             sdst += C::SEGS_PER_ROUND * 256;
         }
-        if ((XV & 16) && it + 1 < n_it) {           // the same, behind the stores (p is dead: fewer live registers)
-            mbar_wait(st_bar, phase);
-            load_round(st_off);
-        }
         seg += C::SEGS_PER_ROUND;
     }
 
@@ -611,7 +579,7 @@ __device__ __forceinline__ void spectro_reg256_v8_body(const SpectroArgs& a) {
     __syncthreads();
     float* red = reinterpret_cast<float*>(dyn_smem);
 #pragma unroll
-    for (int k2 = 0; k2 < 16; ++k2) red[hwi * 256 + 16 * k2 + j] = (XV & 4) ? ((k2 & 1) ? c_im(acc2[k2 >> 1]) : c_re(acc2[k2 >> 1])) : acc[k2];
+    for (int k2 = 0; k2 < 16; ++k2) red[hwi * 256 + 16 * k2 + j] = acc[k2];
     __syncthreads();
     float* pd = a.part + ((size_t)s * a.n_chunks + blockIdx.x) * 256;
     for (int fi = tid; fi < 256; fi += C::THREADS) {
@@ -622,9 +590,9 @@ __device__ __forceinline__ void spectro_reg256_v8_body(const SpectroArgs& a) {
     }
 }
 
-template <bool STORE, int TG = 2, int XV = 0>
+template <bool STORE, int TG = 2>
 __global__ void __launch_bounds__(R256v7::THREADS, 4) spectro_reg256_v8(SpectroArgs a) {
-    spectro_reg256_v8_body<STORE, TG, XV>(a);
+    spectro_reg256_v8_body<STORE, TG>(a);
 }
 
 }  // namespace rt

@@ -174,8 +174,9 @@ int main(int argc, char** argv) {
     run_k(c, spectro_reg256_v7n<true>, R256v7::THREADS, R256v7::SMEM, "v7n", 192);
     run_k(c, spectro_reg256_v7n<true, 2>, R256v7::THREADS, R256v7::SMEM, "v7n TG2", 192);
     run_k(c, spectro_reg256_v7n<true, 2, true>, R256v7::THREADS, R256v7T<4, 4, true>::SMEM, "v7n TG2 LMAP", 192);
-#define RUN8(XV) run_k(c, spectro_reg256_v8<true, 2, XV>, R256v7::THREADS, R256v7T<4, 4, true>::SMEM, "v7n TG2 LMAP -> v8 xv" #XV, 192)
-    RUN8(0); RUN8(8); RUN8(16); RUN8(24); RUN8(9);
+    run_k(c, spectro_reg256_v8<true, 2>, R256v7::THREADS, R256v7T<4, 4, true>::SMEM, "v8 TG2 (the engine's kernel)", 192);
+    run_k(c, spectro_reg256_v8<false, 2>, R256v7::THREADS, R256v7T<4, 4, true>::SMEM, "v8 TG2 no store", 192);
+    run_k(c, spectro_reg256_v8<true, 1>, R256v7::THREADS, R256v7T<4, 4, true>::SMEM, "v8 TG1", 192);
     run_k(c, spectro_reg256_v7n<true, 1, true>, R256v7::THREADS, R256v7T<4, 4, true>::SMEM, "v7n TG1 LMAP", 192);
     run_k(c, spectro_reg256_v7n<true, 4>, R256v7::THREADS, R256v7::SMEM, "v7n TG4", 192);
     run_k(c, spectro_reg256_v7n<true, 8>, R256v7::THREADS, R256v7::SMEM, "v7n TG8", 192);
