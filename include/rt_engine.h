@@ -41,7 +41,11 @@ enum {
     RT_FFT_AUTO = 0,      /* nperseg 256: RT_FFT_REG256; 1024 / 4096: radix-16 Stockham kernel (spectro_r16.cuh); otherwise RT_FFT_GENERIC */
     RT_FFT_GENERIC = 1,   /* shared-memory Stockham FFT, any power-of-two nperseg */
     RT_FFT_REG256 = 2,    /* nperseg 256: 16x16 FFT in registers (packed fp32x2), TMA-fed */
-    RT_FFT_TC256 = 3      /* nperseg 256, boxcar/hann/hamming: first FFT stage on the tensor cores (tcgen05, fp16 x split-fp16 -> fp32) */
+    RT_FFT_TC256 = 3      /* nperseg 256, boxcar/hann/hamming: first FFT stage on the tensor cores (tcgen05, fp16 x split-fp16 -> fp32).
+                           * Optional and slower than the default.  Accuracy limit: the bytes are centred at the constant 128 and the
+                           * rest of the segment mean is removed from the bins 0 and +-1 afterwards, so captures whose DC offset is far
+                           * from 128 (tens of LSB) lose precision in exactly those three bins (tests/test_gpu_parity.py, extreme byte
+                           * patterns); the default kernels subtract the exact mean per sample and have no such limit. */
 };
 
 /* scan_schedule: where the scan kernels (row mean, probe, extraction) of a launch run. */

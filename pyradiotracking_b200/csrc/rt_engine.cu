@@ -684,7 +684,7 @@ __global__ void untile_kernel(const float* S, float* out, int total, int n, floa
 // ---------------------------------------------------------------------------------------------
 #ifdef RT_LAB
 // tools/ only (tools/build_lab_lib.sh, never the shipped library): leave scan kernels out to time what each one costs the step
-extern "C" { int rt_lab_extract_mode = 0; int rt_lab_skip = 0; int rt_lab_lean_per_sm = 0; int rt_lab_extract_per_sm = 0; int rt_lab_s256 = 0; int rt_lab_probe_ppt = 0; }      // skip: bit 0 row means, bit 1 probe, bit 2 extraction; lean CTAs per SM (0 = default)
+extern "C" { int rt_lab_nowait = 0; int rt_lab_extract_mode = 0; int rt_lab_skip = 0; int rt_lab_lean_per_sm = 0; int rt_lab_extract_per_sm = 0; int rt_lab_s256 = 0; int rt_lab_probe_ppt = 0; }      // skip: bit 0 row means, bit 1 probe, bit 2 extraction; lean CTAs per SM (0 = default)
 #define RT_LAB_SKIP(b) (rt_lab_skip & (b))
 #else
 #define RT_LAB_SKIP(b) 0
@@ -1147,6 +1147,10 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     // Two streams: the spectrogram of this launch runs on the launch stream while the scan kernels of the
     // previous launch are still busy on the scan stream.  The buffers this launch writes (S[next], part[slot])
     // were last read by the scan of launch i-2, whose completion event is done[slot].
+#ifdef RT_LAB
+    if (rt_lab_nowait) {}      // timing only (racy): is the scan chain of launch i - 2 the critical path of launch i?
+    else
+#endif
     if (e->launch_seq >= RT_SLOTS && e->scan_stream) CU(cudaStreamWaitEvent(st, e->done[slot], 0));
 
     rt_engine::EvSet* evs = nullptr;

@@ -124,10 +124,17 @@ def test_register_fft_dataflow_on_cpu(tmp_path):
     exe = tmp_path / "hostcheck"
     subprocess.run(["g++", "-O2", "-o", str(exe), os.path.join(ROOT, "tests", "csrc_host_check.cpp")], check=True)
     rng = np.random.default_rng(3)
-    for trial in range(4):
+    for trial in range(6):
         raw = synth.make_stream(synth.C1, 40 + trial, 1)[0][trial * 512: trial * 512 + 512].copy()
         if trial == 3:
             raw = rng.integers(0, 256, 512).astype(np.uint8)           # full-scale bytes
+        if trial == 4:
+            raw[:] = 255                                               # largest byte sums (the packed fields must not overflow)
+            raw[7] = 0                                                 # (one sample off the constant, so that the spectrum is not all zero)
+        if trial == 5:
+            raw[0::2] = 255                                            # I at full scale, Q at zero: the two sum fields stay apart
+            raw[1::2] = 0
+            raw[9] = 3
         win = R.resolve_window("hamming", 256).astype(np.float32)
         out = subprocess.run([str(exe)], input=raw.tobytes() + win.tobytes(), capture_output=True, check=True).stdout
         got = np.frombuffer(out, np.float32).astype(np.float64)

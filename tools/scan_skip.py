@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-VARIANTS = [("all kernels", 0), ("no extraction", 4), ("no probe, no extraction", 6), ("spectrogram only", 7), ("no probe (extraction finds an empty list)", 2)]
+VARIANTS = [("all kernels", 0), ("no row-mean kernel (stale means)", 1), ("no extraction", 4), ("no probe, no extraction", 6), ("spectrogram only", 7), ("no probe (extraction finds an empty list)", 2)]
 
 
 def main():
@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--extract-mode", type=int, nargs="*", default=[0], help="bit 0: no statistics, bit 1: walks read an L2-resident S, bit 2: first block only")
     ap.add_argument("--extract-per-sm", type=int, nargs="*", default=[0])
     ap.add_argument("--lean-per-sm", type=int, nargs="*", default=[0], help="lean scan CTAs per SM to sweep (0 = the engine's default)")
+    ap.add_argument("--nowait", type=int, default=0, help="1: launch i does not wait for the scan of launch i - 2 (racy, timing only)")
     args = ap.parse_args()
     import torch
 
@@ -39,6 +40,7 @@ def main():
     lean = ctypes.c_int.in_dll(lib, "rt_lab_lean_per_sm")
     exps = ctypes.c_int.in_dll(lib, "rt_lab_extract_per_sm")
     xmode = ctypes.c_int.in_dll(lib, "rt_lab_extract_mode")
+    ctypes.c_int.in_dll(lib, "rt_lab_nowait").value = args.nowait
     for per_sm, ex_sm, xm in [(p, x, m) for p in args.lean_per_sm for x in args.extract_per_sm for m in args.extract_mode]:
       lean.value = per_sm
       xmode.value = xm
