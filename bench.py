@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--profile", action="store_true", help="device-resident region only (for runs under ncu)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed batch")
     ap.add_argument("--chunk-segs", type=int, default=-1, help="rt_config.chunk_segs (segments per spectrogram CTA); -1 = the workload's default")
+    ap.add_argument("--scan-schedule", default="auto", choices=["auto", "serial", "overlap", "lean"], help="rt_config.scan_schedule")
+    ap.add_argument("--bpl", type=int, default=0, help="c4: callback blocks per launch (rt_config.blocks_per_launch; 0 = the workload's default, 10)")
     ap.add_argument("--fft-impl", default="auto", choices=["auto", "reg256", "tc256", "generic"],
                     help="spectrogram kernel: auto = reg256 (registers, packed fp32x2); tc256 = tensor-core stage 1 (tcgen05)")
     return ap.parse_args()
@@ -91,7 +93,7 @@ class Work:
 def analyzer_kwargs(wk, rank):
     w, n = wk.w, wk.streams
     return dict(
-        chunk_segs=wk.chunk_segs,
+        chunk_segs=wk.chunk_segs, scan_schedule=getattr(wk, "scan_schedule", 0),
         devices=[str(rank * n + i) for i in range(n)], calibration_db=[0.0] * n,
         sample_rate=w.sample_rate, center_freq=w.center_freq, fft_nperseg=w.nperseg, fft_window="hamming",
         signal_min_duration_ms=w.signal_min_duration_ms, signal_max_duration_ms=w.signal_max_duration_ms,
@@ -358,6 +360,15 @@ def run_b200(args):
     wk = Work(args.workload, args.streams)
     if args.chunk_segs >= 0:
         wk.chunk_segs = args.chunk_segs
+    if args.bpl > 0 and wk.key == "c4":
+        if wk.n_blk % args.bpl:
+            raise SystemExit(f"--bpl must divide the {wk.n_blk}-block chunk")
+        wk.bpl = args.bpl
+        wk.groups = wk.n_blk // wk.bpl
+        wk.samples_per_step = wk.streams * wk.bpl * wk.w.block_samples
+        wk.bytes_per_step = 2 * wk.samples_per_step
+        wk.label = wk.label.replace("10 blocks per launch", f"{wk.bpl} blocks per launch")
+    wk.scan_schedule = {"auto": 0, "serial": 1, "overlap": 2, "lean": 3}[args.scan_schedule]
     S = wk.streams
 
     # every rank keeps to its own share of the host cores: the generator pool, the CUDA driver threads, the finaliser
@@ -524,6 +535,7 @@ def run_b200(args):
             "dtype": "f32", "data": "synthetic",
             "config": wk.config(l2=f"inputs larger than L2 ({wk.bytes_per_step / 1e6:.0f} MB per step, {G} alternating launches)",
                                 records_per_step=n_rec, extract_work_items_per_step=work_items, fft_impl=args.fft_impl, chunk_segs=wk.chunk_segs,
+                                scan_schedule=args.scan_schedule,
                                 host_cores_per_rank=n_cores, cpu_affinity=("all" if affinity is None else f"{affinity[0]}-{affinity[-1]}")),
             "ms_per_step_per_rank": {"min": min(ms_ranks) / args.steps, "median": statistics.median(ms_ranks) / args.steps,
                                      "max": max(ms_ranks) / args.steps, "all": [round(x / args.steps, 5) for x in ms_ranks]},
