@@ -1248,6 +1248,9 @@ int rt_engine_launch(rt_engine* e, const uint8_t* iq, int32_t iq_on_device, size
     if (rt_lab_probe_ppt > 0) ppt = rt_lab_probe_ppt;
 #endif
     dim3 pgrid(((e->n + pbins - 1) / pbins) * ((e->n_probes + ppt - 1) / ppt), e->n_units);
+#ifdef RT_LAB
+    if (rt_lab_extract_mode & 16) sc.stream_stride = 0;    // timing only: the probe (and the walks) read unit 0's S, which stays in L2
+#endif
 #define RT_PROBE(L)                                                                        \
     do {                                                                                   \
         if (lean) probe_lean_kernel<L><<<e->lean_ctas, 128, 0, sc_st>>>(sc);               \
