@@ -4,8 +4,8 @@ import torch
 from pyradiotracking_b200 import synth
 from pyradiotracking_b200.analyze import BatchAnalyzer
 from tools.bench_configs import run
-for rep in range(2):
-    for ch in (160, 176, 192, 208, 224, 240, 312):
+for rep in range(3):
+    for ch in (128, 144, 160, 176, 192):
         buf = io.StringIO()
         with contextlib.redirect_stdout(buf):
             run(f"chunk {ch}", synth.C2, 64, 40, 4, torch, synth, BatchAnalyzer, kernel_timing=0, chunk_segs=ch)
