@@ -325,4 +325,10 @@ template <bool STORE, int W, int MB>
 __global__ void __launch_bounds__(32 * W, MB) spectro_reg256_v7w(SpectroArgs a) {
     spectro_reg256_v7_body<STORE, false, false, false, false, false, 0, true, false, R256v7T<W, MB>>(a);
 }
+
+// v8 with a register cap: would a third lean scan CTA fit beside four spectrogram CTAs (104 registers leave 12288 of an SM's 65536)?
+template <bool STORE, int MAXR>
+__global__ void __maxnreg__(MAXR) spectro_reg256_v8r(SpectroArgs a) {
+    spectro_reg256_v8_body<STORE, 2>(a);
+}
 }  // namespace rt

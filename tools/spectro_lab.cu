@@ -175,6 +175,8 @@ int main(int argc, char** argv) {
     run_k(c, spectro_reg256_v7n<true, 2>, R256v7::THREADS, R256v7::SMEM, "v7n TG2", 192);
     run_k(c, spectro_reg256_v7n<true, 2, true>, R256v7::THREADS, R256v7T<4, 4, true>::SMEM, "v7n TG2 LMAP", 192);
     run_k(c, spectro_reg256_v8<true, 2>, R256v7::THREADS, R256v7T<4, 4, true>::SMEM, "v8 TG2 (the engine's kernel)", 192);
+    run_k(c, spectro_reg256_v8r<true, 104>, R256v7::THREADS, R256v7T<4, 4, true>::SMEM, "v8 TG2 maxnreg 104", 192);
+    run_k(c, spectro_reg256_v8r<true, 96>, R256v7::THREADS, R256v7T<4, 4, true>::SMEM, "v8 TG2 maxnreg 96", 192);
     run_k(c, spectro_reg256_v8<false, 2>, R256v7::THREADS, R256v7T<4, 4, true>::SMEM, "v8 TG2 no store", 192);
     run_k(c, spectro_reg256_v8<true, 1>, R256v7::THREADS, R256v7T<4, 4, true>::SMEM, "v8 TG1", 192);
     run_k(c, spectro_reg256_v7n<true, 1, true>, R256v7::THREADS, R256v7T<4, 4, true>::SMEM, "v7n TG1 LMAP", 192);
